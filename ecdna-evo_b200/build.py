@@ -1,0 +1,49 @@
+"""In-tree build of libecdna_b200.so (nvcc, sm_100a only) and of the C++ host CLI."""
+import os
+import shutil
+import subprocess
+
+PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(PKG_DIR)
+LIB_PATH = os.path.join(PKG_DIR, "libecdna_b200.so")
+CLI_PATH = os.path.join(PKG_DIR, "host", "ecdna")
+CSRC = os.path.join(PKG_DIR, "csrc")
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared",
+              "-Xcompiler", "-fPIC", "-cudart", "static", "-diag-suppress", "128"]
+
+
+def _nvcc():
+    for cand in (shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found: libecdna_b200.so cannot be built (there is no CPU fallback)")
+
+
+def _stale(target, sources):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(s) > t for s in sources)
+
+
+def build(force=False, verbose=False):
+    """Compile csrc/*.cu into libecdna_b200.so and host/*.cpp into the `ecdna` CLI."""
+    srcs = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC))] + [os.path.join(ROOT, "include", "ecdna_b200.h")]
+    if force or _stale(LIB_PATH, srcs):
+        cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + [
+            "-o", LIB_PATH, os.path.join(CSRC, "capi.cu")]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
+        if verbose:
+            print(r.stderr)
+    host_dir = os.path.join(PKG_DIR, "host")
+    host_srcs = [os.path.join(host_dir, f) for f in sorted(os.listdir(host_dir)) if f.endswith((".cpp", ".h"))]
+    if host_srcs and (force or _stale(CLI_PATH, host_srcs + [LIB_PATH])):
+        cmd = ["g++", "-O2", "-std=c++17", "-I", os.path.join(ROOT, "include"), "-o", CLI_PATH] + [
+            s for s in host_srcs if s.endswith(".cpp")] + ["-L", PKG_DIR, "-lecdna_b200", "-Wl,-rpath,$ORIGIN/..",
+                                                            "-ldl", "-lpthread"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("g++ (host CLI) failed:\n" + r.stdout + r.stderr)
+    return LIB_PATH

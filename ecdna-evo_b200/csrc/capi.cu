@@ -1,0 +1,523 @@
+// capi.cu -- the C ABI of libecdna_b200.so (include/ecdna_b200.h) over the SSA kernel.
+//
+// One context = one GPU, one stream, grow-only device buffers.  There is no CPU path: without an
+// sm_100 device every entry point fails with ECDNA_B200_ERR_NO_DEVICE / ECDNA_B200_ERR_CUDA.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "ssa_kernel.cuh"
+
+using namespace ecdna;
+
+namespace {
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t bytes, bool zero_new = false) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) return e;
+    cap = bytes;
+    if (zero_new) e = cudaMemset(p, 0, bytes);
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+// the per-run result columns, in the order of ecdna_b200_results_t
+enum Col {
+  C_STOP, C_NMINUS, C_NPLUS, C_TIME, C_NEVENTS, C_KMAX, C_MEAN, C_FREQ, C_ENT, C_VAR, C_ABCD, C_ABCA, C_HASH,
+  C_CHAIN, C_HIST, C_SNAPCOUNT, C_SNAPCELLS, C_SNAPTIME, C_SNAPHIST, C_DYNCOUNT, C_DYN, C_SUMK, C_NDIV, C_NDEATH,
+  C_COUNT
+};
+
+}  // namespace
+
+struct ecdna_b200_ctx {
+  int device = 0;
+  int sm_count = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev_begin = nullptr, ev_k0 = nullptr, ev_k1 = nullptr, ev_end = nullptr;
+  bool have_total = false;
+  std::string err;
+  DevBuf init_k, init_c, snap, rates, replay, replay_off, abc_cdf, arena, counters, scratch, cols[C_COUNT];
+  size_t arena_tiles = 0, arena_kcap = 0;
+  ecdna_b200_timing_t timing{};
+};
+
+namespace {
+
+int fail(ecdna_b200_ctx* ctx, int code, const std::string& msg) {
+  if (ctx) ctx->err = msg;
+  return code;
+}
+#define CU(call)                                                                                  \
+  do {                                                                                            \
+    cudaError_t e__ = (call);                                                                     \
+    if (e__ != cudaSuccess)                                                                       \
+      return fail(ctx, ECDNA_B200_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__)); \
+  } while (0)
+
+template <int L, bool REPLAY>
+int launch_one(ecdna_b200_ctx* ctx, SsaArgs& a, cudaStream_t st, const ecdna_b200_params_t* p) {
+  auto kern = ssa_kernel<L, REPLAY>;
+  const int tiles_per_block = kBlockThreads / L;
+  const size_t smem = (size_t)tiles_per_block * a.kcap_s * sizeof(uint32_t);
+  if (smem > 200 * 1024) return fail(ctx, ECDNA_B200_ERR_BAD_PARAMS, "smem_bins too large for one block");
+  CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int bps = 0;
+  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, kBlockThreads, smem));
+  if (bps < 1) return fail(ctx, ECDNA_B200_ERR_BAD_PARAMS, "kernel does not fit on an SM");
+  const uint64_t need = ((uint64_t)a.n_runs + tiles_per_block - 1) / tiles_per_block;
+  uint64_t grid = (uint64_t)ctx->sm_count * bps;
+  if (need < grid) grid = need;
+  if (grid == 0) grid = 1;
+  // HBM arena: one window of kcap_g bins per resident tile, kept zeroed between replicates
+  a.arena = nullptr;
+  if (p->state_mode != ECDNA_B200_STATE_SMEM) {
+    const size_t tiles = (size_t)ctx->sm_count * bps * tiles_per_block;
+    if (tiles * a.kcap_g > ctx->arena_tiles * ctx->arena_kcap || a.kcap_g != ctx->arena_kcap) {
+      CU(ctx->arena.ensure(tiles * a.kcap_g * sizeof(uint32_t)));
+      CU(cudaMemsetAsync(ctx->arena.p, 0, tiles * a.kcap_g * sizeof(uint32_t), st));
+      ctx->arena_tiles = tiles;
+      ctx->arena_kcap = a.kcap_g;
+    }
+    a.arena = (uint32_t*)ctx->arena.p;
+  }
+  CU(cudaEventRecord(ctx->ev_k0, st));
+  kern<<<(unsigned)grid, kBlockThreads, smem, st>>>(a);
+  CU(cudaGetLastError());
+  CU(cudaEventRecord(ctx->ev_k1, st));
+  ctx->timing.kernel_launches = 1;
+  ctx->timing.tile_width = L;
+  ctx->timing.smem_bins = a.kcap_s;
+  ctx->timing.grid_blocks = (uint32_t)grid;
+  ctx->timing.block_threads = kBlockThreads;
+  ctx->timing.blocks_per_sm = (uint32_t)bps;
+  return ECDNA_B200_OK;
+}
+
+// target statistics for the ABC epilogue, same definitions as the device epilogue
+void target_stats(const std::vector<uint64_t>& h, float* mean, float* ent, float* freq, std::vector<float>* cdf) {
+  uint64_t n = 0, s1 = 0;
+  for (size_t k = 0; k < h.size(); ++k) { n += h[k]; s1 += (uint64_t)k * h[k]; }
+  cdf->assign(h.size(), 1.0f);
+  *mean = *ent = *freq = 0.f;
+  if (n == 0) return;
+  const float nf = (float)n;
+  *mean = (float)s1 / nf;
+  *freq = (float)(n - h[0]) / nf;
+  float e = 0.f;
+  uint64_t cum = 0;
+  for (size_t k = 0; k < h.size(); ++k) {
+    if (h[k]) { const float pk = (float)h[k] / nf; e -= pk * log2f(pk); }
+    cum += h[k];
+    (*cdf)[k] = (float)cum / nf;
+  }
+  *ent = e;
+}
+
+size_t col_bytes(int c, const ecdna_b200_params_t* p, uint32_t stride) {
+  switch (c) {
+    case C_STOP: case C_KMAX: case C_SNAPCOUNT: case C_DYNCOUNT: case C_NDIV: case C_NDEATH: return 4;
+    case C_NMINUS: case C_NPLUS: case C_NEVENTS: case C_HASH: case C_CHAIN: case C_SUMK: return 8;
+    case C_TIME: case C_MEAN: case C_FREQ: case C_ENT: case C_VAR: return 4;
+    case C_ABCD: return 16;
+    case C_ABCA: return 1;
+    case C_HIST: return (size_t)stride * 4;
+    case C_SNAPCELLS: return (size_t)p->n_snapshots * 8;
+    case C_SNAPTIME: return (size_t)p->n_snapshots * 4;
+    case C_SNAPHIST: return (size_t)p->n_snapshots * stride * 4;
+    case C_DYN: return (size_t)p->dyn_points * 5 * 4;
+  }
+  return 0;
+}
+void** col_slot(ecdna_b200_results_t* r, int c) {
+  switch (c) {
+    case C_STOP: return (void**)&r->stop_reason;
+    case C_NMINUS: return (void**)&r->nminus;
+    case C_NPLUS: return (void**)&r->nplus;
+    case C_TIME: return (void**)&r->time;
+    case C_NEVENTS: return (void**)&r->n_events;
+    case C_KMAX: return (void**)&r->kmax;
+    case C_MEAN: return (void**)&r->mean;
+    case C_FREQ: return (void**)&r->frequency;
+    case C_ENT: return (void**)&r->entropy;
+    case C_VAR: return (void**)&r->variance;
+    case C_ABCD: return (void**)&r->abc_distance;
+    case C_ABCA: return (void**)&r->abc_accept;
+    case C_HASH: return (void**)&r->hash;
+    case C_CHAIN: return (void**)&r->chain;
+    case C_HIST: return (void**)&r->hist;
+    case C_SNAPCOUNT: return (void**)&r->snap_count;
+    case C_SNAPCELLS: return (void**)&r->snap_cells;
+    case C_SNAPTIME: return (void**)&r->snap_time;
+    case C_SNAPHIST: return (void**)&r->snap_hist;
+    case C_DYNCOUNT: return (void**)&r->dyn_count;
+    case C_DYN: return (void**)&r->dyn;
+    case C_SUMK: return (void**)&r->sum_k;
+    case C_NDIV: return (void**)&r->n_div;
+    case C_NDEATH: return (void**)&r->n_death;
+  }
+  return nullptr;
+}
+
+int validate(ecdna_b200_ctx* ctx, const ecdna_b200_params_t* p, uint64_t n_runs) {
+  if (!p) return fail(ctx, ECDNA_B200_ERR_BAD_PARAMS, "params is NULL");
+  if (p->abi_version != ECDNA_B200_ABI_VERSION) return fail(ctx, ECDNA_B200_ERR_BAD_PARAMS, "abi_version mismatch");
+  if (n_runs == 0 || n_runs >= 0xFFFFFFF0ull) return fail(ctx, ECDNA_B200_ERR_BAD_PARAMS, "n_runs must be in [1, 2^32)");
+  const float r[4] = {p->b0, p->b1, p->d0, p->d1};
+  for (float v : r)
+    if (!(v >= 0.f)) return fail(ctx, ECDNA_B200_ERR_BAD_PARAMS, "rates must be >= 0 (Exp::new panics otherwise)");
+  if (p->segregation > 3) return fail(ctx, ECDNA_B200_ERR_BAD_PARAMS, "unknown segregation rule");
+  if (p->max_cells == 0 || p->max_cells >= (1ull << 32)) return fail(ctx, ECDNA_B200_ERR_BAD_PARAMS, "max_cells must be in [1, 2^32)");
+  if (p->max_iter == 0 || p->max_iter >= (1ull << 32)) return fail(ctx, ECDNA_B200_ERR_BAD_PARAMS, "max_iter must be in [1, 2^32)");
+  if (p->n_init == 0 || !p->init_k || !p->init_c) return fail(ctx, ECDNA_B200_ERR_BAD_PARAMS, "empty initial distribution (ensure!(!distribution.is_empty()), process.rs:88)");
+  if (p->n_snapshots && !p->snapshot_cells) return fail(ctx, ECDNA_B200_ERR_BAD_PARAMS, "snapshot_cells is NULL");
+  if (p->rng_mode > 1) return fail(ctx, ECDNA_B200_ERR_BAD_PARAMS, "unknown rng_mode");
+  if (p->rng_mode == ECDNA_B200_RNG_REPLAY && (!p->replay || !p->replay_offsets)) return fail(ctx, ECDNA_B200_ERR_BAD_PARAMS, "replay mode needs replay and replay_offsets");
+  if (p->state_mode > 2) return fail(ctx, ECDNA_B200_ERR_BAD_PARAMS, "unknown state_mode");
+  if (p->tile_width != 0 && p->tile_width != 8 && p->tile_width != 16 && p->tile_width != 32) return fail(ctx, ECDNA_B200_ERR_BAD_PARAMS, "tile_width must be 8, 16 or 32");
+  if (p->max_copies > 65535) return fail(ctx, ECDNA_B200_ERR_BAD_PARAMS, "max_copies must be <= 65535 (DNACopy is u16)");
+  if (p->abc_enabled && (!p->abc_target_hist || p->abc_target_len == 0)) return fail(ctx, ECDNA_B200_ERR_BAD_PARAMS, "abc_enabled needs a target distribution");
+  if (p->dyn_points && !(p->dyn_dt > 0.f)) return fail(ctx, ECDNA_B200_ERR_BAD_PARAMS, "dyn_dt must be > 0");
+  return ECDNA_B200_OK;
+}
+
+// device_io: results and the bulk inputs are device pointers already
+int run_common(ecdna_b200_ctx* ctx, const ecdna_b200_params_t* p, uint64_t idx_begin, uint64_t n_runs,
+               const ecdna_b200_results_t* results, cudaStream_t st, bool device_io) {
+  int rc = validate(ctx, p, n_runs);
+  if (rc) return rc;
+  if (!results) return fail(ctx, ECDNA_B200_ERR_BAD_PARAMS, "results is NULL");
+  CU(cudaSetDevice(ctx->device));
+  ecdna_b200_timing_t& tm = ctx->timing;
+  tm = ecdna_b200_timing_t{};
+  ctx->have_total = !device_io;
+
+  SsaArgs a{};
+  a.rate[0] = p->b0; a.rate[1] = p->b1; a.rate[2] = p->d0; a.rate[3] = p->d1;
+  a.segregation = p->segregation;
+  const bool birth_death = p->d0 > 0.f || p->d1 > 0.f;  // clap_app.rs:165-174
+  a.cells_stop = (uint32_t)((p->bd_count_mode == 1 && birth_death) ? (p->max_cells + 1) / 2 : p->max_cells);
+  a.max_iter_m1 = (uint32_t)(p->max_iter - 1);
+  a.max_time = p->max_time;
+  a.seed_lo = (uint32_t)p->seed; a.seed_hi = (uint32_t)(p->seed >> 32);
+  a.idx_begin = idx_begin;
+  a.n_runs = (uint32_t)n_runs;
+  a.dyn_points = p->dyn_points; a.dyn_dt = p->dyn_dt;
+  a.state_mode = p->state_mode;
+  a.flags = p->flags;
+  a.kcap_s = p->smem_bins ? ((p->smem_bins + 31u) & ~31u) : 512u;
+  a.kcap_g = ((p->max_copies ? p->max_copies : 65535u) + 32u) & ~31u;
+  if (a.kcap_g < a.kcap_s) a.kcap_g = a.kcap_s;
+  a.hist_stride = p->hist_stride ? p->hist_stride : 512u;
+  const uint32_t stride = a.hist_stride;
+
+  if (!device_io) CU(cudaEventRecord(ctx->ev_begin, st));
+
+  // ---- small inputs: initial distribution, snapshot sizes (always host pointers) ----
+  std::vector<uint32_t> ik, ic;
+  uint64_t nminus0 = 0;
+  for (uint32_t i = 0; i < p->n_init; ++i) {
+    if (p->init_c[i] == 0) continue;
+    if (p->init_c[i] >= (1ull << 32)) return fail(ctx, ECDNA_B200_ERR_BAD_PARAMS, "initial count too large");
+    if (p->init_k[i] == 0) { nminus0 += p->init_c[i]; continue; }
+    if (p->init_k[i] >= a.kcap_g) return fail(ctx, ECDNA_B200_ERR_BAD_PARAMS, "initial copy number beyond max_copies");
+    ik.push_back(p->init_k[i]);
+    ic.push_back((uint32_t)p->init_c[i]);
+  }
+  if (ik.empty() && nminus0 == 0) return fail(ctx, ECDNA_B200_ERR_BAD_PARAMS, "empty initial distribution (ensure!(!distribution.is_empty()), process.rs:88)");
+  a.n_init = (uint32_t)ik.size();
+  a.init_nminus = (uint32_t)nminus0;
+  if (a.n_init) {
+    CU(ctx->init_k.ensure(ik.size() * 4));
+    CU(ctx->init_c.ensure(ic.size() * 4));
+    CU(cudaMemcpyAsync(ctx->init_k.p, ik.data(), ik.size() * 4, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(ctx->init_c.p, ic.data(), ic.size() * 4, cudaMemcpyHostToDevice, st));
+    tm.h2d_bytes += ik.size() * 8;
+  }
+  a.init_k = (const uint32_t*)ctx->init_k.p;
+  a.init_c = (const uint32_t*)ctx->init_c.p;
+  std::vector<uint32_t> snaps;
+  for (uint32_t i = 0; i < p->n_snapshots; ++i)
+    snaps.push_back(p->snapshot_cells[i] >= (1ull << 32) ? 0xFFFFFFFFu : (uint32_t)p->snapshot_cells[i]);
+  a.n_snap = (uint32_t)snaps.size();
+  if (a.n_snap) {
+    CU(ctx->snap.ensure(snaps.size() * 4));
+    CU(cudaMemcpyAsync(ctx->snap.p, snaps.data(), snaps.size() * 4, cudaMemcpyHostToDevice, st));
+    tm.h2d_bytes += snaps.size() * 4;
+  }
+  a.snap_cells = (const uint32_t*)ctx->snap.p;
+
+  // ---- ABC target: statistics and CDF computed once on the host, uploaded ----
+  std::vector<float> cdf;
+  if (p->abc_enabled) {
+    std::vector<uint64_t> th(p->abc_target_len);
+    if (device_io) CU(cudaMemcpyAsync(th.data(), p->abc_target_hist, th.size() * 8, cudaMemcpyDeviceToHost, st));
+    else std::memcpy(th.data(), p->abc_target_hist, th.size() * 8);
+    if (device_io) CU(cudaStreamSynchronize(st));
+    target_stats(th, &a.abc_mean, &a.abc_entropy, &a.abc_freq, &cdf);
+    CU(ctx->abc_cdf.ensure(cdf.size() * 4));
+    CU(cudaMemcpyAsync(ctx->abc_cdf.p, cdf.data(), cdf.size() * 4, cudaMemcpyHostToDevice, st));
+    tm.h2d_bytes += cdf.size() * 4;
+    a.abc = 1;
+    a.abc_cdf = (const float*)ctx->abc_cdf.p;
+    a.abc_len = (uint32_t)cdf.size();
+    for (int i = 0; i < 4; ++i) a.abc_thr[i] = p->abc_thresholds[i];
+  }
+
+  // ---- bulk inputs: per-run rates, replay stream ----
+  if (p->rates_per_run) {
+    if (device_io) a.rates_per_run = p->rates_per_run;
+    else {
+      CU(ctx->rates.ensure(n_runs * 16));
+      CU(cudaMemcpyAsync(ctx->rates.p, p->rates_per_run, n_runs * 16, cudaMemcpyHostToDevice, st));
+      tm.h2d_bytes += n_runs * 16;
+      a.rates_per_run = (const float*)ctx->rates.p;
+    }
+  }
+  const bool replay = p->rng_mode == ECDNA_B200_RNG_REPLAY;
+  if (replay) {
+    if (device_io) { a.replay = p->replay; a.replay_off = p->replay_offsets; }
+    else {
+      const uint64_t total = p->replay_offsets[n_runs];
+      CU(ctx->replay.ensure((size_t)total * sizeof(ecdna_b200_replay_event_t) + 16));
+      CU(ctx->replay_off.ensure((n_runs + 1) * 8));
+      CU(cudaMemcpyAsync(ctx->replay.p, p->replay, (size_t)total * sizeof(ecdna_b200_replay_event_t), cudaMemcpyHostToDevice, st));
+      CU(cudaMemcpyAsync(ctx->replay_off.p, p->replay_offsets, (n_runs + 1) * 8, cudaMemcpyHostToDevice, st));
+      tm.h2d_bytes += total * sizeof(ecdna_b200_replay_event_t) + (n_runs + 1) * 8;
+      a.replay = (const ecdna_b200_replay_event_t*)ctx->replay.p;
+      a.replay_off = (const uint64_t*)ctx->replay_off.p;
+    }
+  }
+
+  // ---- outputs ----
+  ecdna_b200_results_t host = *results, dev = *results;
+  if (!device_io) {
+    for (int c = 0; c < C_COUNT; ++c) {
+      void** hs = col_slot(&host, c);
+      void** ds = col_slot(&dev, c);
+      if (!*hs) continue;
+      const size_t bytes = col_bytes(c, p, stride) * n_runs;
+      if (bytes == 0) { *ds = nullptr; continue; }
+      CU(ctx->cols[c].ensure(bytes));
+      *ds = ctx->cols[c].p;
+      if (c == C_SNAPCELLS || c == C_SNAPTIME || c == C_SNAPHIST || c == C_DYN) CU(cudaMemsetAsync(*ds, 0, bytes, st));
+    }
+  }
+  a.out = dev;
+  CU(ctx->counters.ensure(64));
+  CU(cudaMemsetAsync(ctx->counters.p, 0, 64, st));
+  a.work_counter = (uint32_t*)ctx->counters.p;
+  a.totals = (unsigned long long*)((char*)ctx->counters.p + 8);
+
+  const uint32_t L = p->tile_width ? p->tile_width : 32u;
+  if (L == 32) rc = replay ? launch_one<32, true>(ctx, a, st, p) : launch_one<32, false>(ctx, a, st, p);
+  else if (L == 16) rc = replay ? launch_one<16, true>(ctx, a, st, p) : launch_one<16, false>(ctx, a, st, p);
+  else rc = replay ? launch_one<8, true>(ctx, a, st, p) : launch_one<8, false>(ctx, a, st, p);
+  if (rc) return rc;
+
+  if (!device_io) {
+    for (int c = 0; c < C_COUNT; ++c) {
+      void** hs = col_slot(&host, c);
+      void** ds = col_slot(&dev, c);
+      if (!*hs || !*ds) continue;
+      const size_t bytes = col_bytes(c, p, stride) * n_runs;
+      CU(cudaMemcpyAsync(*hs, *ds, bytes, cudaMemcpyDeviceToHost, st));
+      tm.d2h_bytes += bytes;
+    }
+    CU(cudaEventRecord(ctx->ev_end, st));
+    CU(cudaStreamSynchronize(st));
+  }
+  return ECDNA_B200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// small utility kernels: ABC prior draws, compaction of accepted draws
+// ---------------------------------------------------------------------------------------------
+__global__ void prior_kernel(uint32_t seed_lo, uint32_t seed_hi, uint64_t idx_begin, uint32_t n, float b0, float lo1,
+                             float hi1, float lo2, float hi2, float lo3, float hi3, float* out) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint64_t idx = idx_begin + i;
+  const uint4 x = philox4x32_10(0xABC0ABC0u, 0xFFFFFFFFu, (uint32_t)idx, (uint32_t)(idx >> 32), seed_lo, seed_hi);
+  const float s = 5.9604644775390625e-08f;  // 2^-24
+  const float u1 = __uint2float_rn(x.x >> 8) * s, u2 = __uint2float_rn(x.y >> 8) * s, u3 = __uint2float_rn(x.z >> 8) * s;
+  out[4 * (size_t)i + 0] = b0;
+  out[4 * (size_t)i + 1] = __fmaf_rn(u1, hi1 - lo1, lo1);
+  out[4 * (size_t)i + 2] = __fmaf_rn(u2, hi2 - lo2, lo2);
+  out[4 * (size_t)i + 3] = __fmaf_rn(u3, hi3 - lo3, lo3);
+}
+
+constexpr int kCompactBlock = 1024;
+__global__ void compact_count(const uint8_t* flag, uint32_t n, uint32_t* block_counts) {
+  const uint32_t i = blockIdx.x * kCompactBlock + threadIdx.x;
+  const int c = __syncthreads_count(i < n && flag[i] != 0);
+  if (threadIdx.x == 0) block_counts[blockIdx.x] = (uint32_t)c;
+}
+__global__ void compact_scan(uint32_t* block_counts, uint32_t n_blocks, uint32_t* total) {
+  // single block: exclusive scan of the block counts (n_blocks is small: n_runs / 1024)
+  __shared__ uint32_t carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (uint32_t base = 0; base < n_blocks; base += blockDim.x) {
+    const uint32_t i = base + threadIdx.x;
+    uint32_t v = i < n_blocks ? block_counts[i] : 0u;
+    const uint32_t lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+    uint32_t inc = v;
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t u = __shfl_up_sync(0xFFFFFFFFu, inc, o); if ((int)lane >= o) inc += u; }
+    __shared__ uint32_t wsum[32];
+    if (lane == 31) wsum[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+      uint32_t s = lane < (blockDim.x >> 5) ? wsum[lane] : 0u;
+      uint32_t si = s;
+      for (int o = 1; o < 32; o <<= 1) { const uint32_t u = __shfl_up_sync(0xFFFFFFFFu, si, o); if ((int)lane >= o) si += u; }
+      wsum[lane] = si - s;
+    }
+    __syncthreads();
+    const uint32_t excl = carry + wsum[w] + inc - v;
+    if (i < n_blocks) block_counts[i] = excl;
+    __syncthreads();
+    if (threadIdx.x == blockDim.x - 1) carry = excl + v;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *total = carry;
+}
+__global__ void compact_scatter(const uint8_t* flag, uint32_t n, const uint32_t* block_offsets, uint32_t* out) {
+  const uint32_t i = blockIdx.x * kCompactBlock + threadIdx.x;
+  const bool f = i < n && flag[i] != 0;
+  const uint32_t lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+  const uint32_t b = __ballot_sync(0xFFFFFFFFu, f);
+  __shared__ uint32_t wcount[32];
+  if (lane == 0) wcount[w] = __popc(b);
+  __syncthreads();
+  uint32_t off = block_offsets[blockIdx.x];
+  for (uint32_t j = 0; j < w; ++j) off += wcount[j];
+  if (f) out[off + __popc(b & ((1u << lane) - 1u))] = i;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ecdna_b200_abi_version(void) { return ECDNA_B200_ABI_VERSION; }
+
+int ecdna_b200_create(int device, ecdna_b200_ctx** out) {
+  if (!out) return ECDNA_B200_ERR_BAD_PARAMS;
+  *out = nullptr;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) return ECDNA_B200_ERR_NO_DEVICE;
+  if (device < 0 || device >= count) return ECDNA_B200_ERR_BAD_PARAMS;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return ECDNA_B200_ERR_CUDA;
+  if (prop.major != 10) return ECDNA_B200_ERR_NO_DEVICE;  // the fatbin holds sm_100a code only
+  ecdna_b200_ctx* ctx = new ecdna_b200_ctx();
+  ctx->device = device;
+  ctx->sm_count = prop.multiProcessorCount;
+  if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreate(&ctx->ev_begin) != cudaSuccess || cudaEventCreate(&ctx->ev_k0) != cudaSuccess ||
+      cudaEventCreate(&ctx->ev_k1) != cudaSuccess || cudaEventCreate(&ctx->ev_end) != cudaSuccess) {
+    delete ctx;
+    return ECDNA_B200_ERR_CUDA;
+  }
+  *out = ctx;
+  return ECDNA_B200_OK;
+}
+
+void ecdna_b200_destroy(ecdna_b200_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  DevBuf* bufs[] = {&ctx->init_k, &ctx->init_c, &ctx->snap, &ctx->rates, &ctx->replay, &ctx->replay_off,
+                    &ctx->abc_cdf, &ctx->arena, &ctx->counters, &ctx->scratch};
+  for (DevBuf* b : bufs) b->release();
+  for (auto& b : ctx->cols) b.release();
+  cudaEventDestroy(ctx->ev_begin); cudaEventDestroy(ctx->ev_k0); cudaEventDestroy(ctx->ev_k1); cudaEventDestroy(ctx->ev_end);
+  cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+const char* ecdna_b200_last_error(const ecdna_b200_ctx* ctx) { return ctx ? ctx->err.c_str() : "no context"; }
+
+int ecdna_b200_run(ecdna_b200_ctx* ctx, const ecdna_b200_params_t* params, uint64_t idx_begin, uint64_t n_runs,
+                   const ecdna_b200_results_t* results) {
+  if (!ctx) return ECDNA_B200_ERR_BAD_PARAMS;
+  return run_common(ctx, params, idx_begin, n_runs, results, ctx->stream, false);
+}
+
+int ecdna_b200_run_device(ecdna_b200_ctx* ctx, const ecdna_b200_params_t* params, uint64_t idx_begin, uint64_t n_runs,
+                          const ecdna_b200_results_t* results, void* cuda_stream) {
+  if (!ctx) return ECDNA_B200_ERR_BAD_PARAMS;
+  return run_common(ctx, params, idx_begin, n_runs, results, cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream, true);
+}
+
+int ecdna_b200_get_timing(ecdna_b200_ctx* ctx, ecdna_b200_timing_t* t) {
+  if (!ctx || !t) return ECDNA_B200_ERR_BAD_PARAMS;
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaEventSynchronize(ctx->ev_k1));
+  CU(cudaEventElapsedTime(&ctx->timing.kernel_ms, ctx->ev_k0, ctx->ev_k1));
+  if (ctx->have_total) {
+    CU(cudaEventSynchronize(ctx->ev_end));
+    CU(cudaEventElapsedTime(&ctx->timing.total_ms, ctx->ev_begin, ctx->ev_end));
+  }
+  unsigned long long tot[5];
+  CU(cudaMemcpy(tot, (char*)ctx->counters.p + 8, sizeof tot, cudaMemcpyDeviceToHost));
+  ctx->timing.total_events = tot[0];
+  // division = 4K + 24 + 16, death = 4K + 8 + 16, ecDNA- event = 16 bytes
+  ctx->timing.alg_bytes = 4ull * tot[1] + 24ull * tot[2] + 8ull * tot[3] + 16ull * tot[0];
+  ctx->timing.n_spilled = (uint32_t)tot[4];
+  *t = ctx->timing;
+  return ECDNA_B200_OK;
+}
+
+int ecdna_b200_abc_draw_priors(ecdna_b200_ctx* ctx, uint64_t seed, uint64_t idx_begin, uint64_t n_runs, float b0,
+                               const float b1_range[2], const float d0_range[2], const float d1_range[2],
+                               float* rates_out) {
+  if (!ctx || !rates_out || n_runs == 0 || n_runs >= (1ull << 32)) return fail(ctx, ECDNA_B200_ERR_BAD_PARAMS, "bad prior request");
+  CU(cudaSetDevice(ctx->device));
+  CU(ctx->rates.ensure(n_runs * 16));
+  const uint32_t n = (uint32_t)n_runs;
+  prior_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>((uint32_t)seed, (uint32_t)(seed >> 32), idx_begin, n, b0,
+                                                         b1_range[0], b1_range[1], d0_range[0], d0_range[1],
+                                                         d1_range[0], d1_range[1], (float*)ctx->rates.p);
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(rates_out, ctx->rates.p, n_runs * 16, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return ECDNA_B200_OK;
+}
+
+int ecdna_b200_compact_accepted(ecdna_b200_ctx* ctx, const uint8_t* accept_dev, uint64_t n_runs,
+                                uint32_t* accepted_idx_dev, uint32_t* n_accepted, void* cuda_stream) {
+  if (!ctx || !accept_dev || !accepted_idx_dev || !n_accepted || n_runs == 0 || n_runs >= (1ull << 32))
+    return fail(ctx, ECDNA_B200_ERR_BAD_PARAMS, "bad compaction request");
+  CU(cudaSetDevice(ctx->device));
+  cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
+  const uint32_t n = (uint32_t)n_runs;
+  const uint32_t nb = (n + kCompactBlock - 1) / kCompactBlock;
+  CU(ctx->scratch.ensure(((size_t)nb + 1) * 4));  // block counts + total
+  uint32_t* counts = (uint32_t*)ctx->scratch.p;
+  compact_count<<<nb, kCompactBlock, 0, st>>>(accept_dev, n, counts);
+  compact_scan<<<1, 1024, 0, st>>>(counts, nb, counts + nb);
+  compact_scatter<<<nb, kCompactBlock, 0, st>>>(accept_dev, n, counts, accepted_idx_dev);
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(n_accepted, counts + nb, 4, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  return ECDNA_B200_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,207 @@
+/*
+ * ecdna_b200.h -- C ABI of libecdna_b200.so, the B200 (sm_100a) backend for ecdna-evo's hot path.
+ *
+ * The reference has no FFI; its seam is the per-replicate closure `run_simulations(idx)`
+ * (reference src/main.rs:55-211) that rayon maps over idx in [seed*10, seed*10+runs)
+ * (main.rs:214-225).  One call of ecdna_b200_run() replaces that closure for a whole index range:
+ * it takes the fields of SimulationOptions (main.rs:28-44) and gives back, per replicate, what the
+ * closure produces: the stop reason, (nminus, nplus), the clock (main.rs:205-210) and the ecDNA
+ * distributions that `save` (src/process.rs:31-55) would have written -- at the end of the run
+ * (main.rs:100-109) and at every snapshot size (process.rs:122-145, 267-290).  Writing the JSON
+ * files stays on the host side.
+ *
+ * Plain C: fixed-width integers, f32 rates (they are f32 in the reference and appear in file
+ * names), caller-owned buffers, int status codes, no exceptions, no aborts.
+ */
+#ifndef ECDNA_B200_H
+#define ECDNA_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ECDNA_B200_ABI_VERSION 1
+
+/* status codes returned by every entry point */
+enum {
+  ECDNA_B200_OK = 0,
+  ECDNA_B200_ERR_BAD_PARAMS = 1,  /* see ecdna_b200_last_error() */
+  ECDNA_B200_ERR_CUDA = 2,        /* a CUDA call failed; never falls back to the CPU */
+  ECDNA_B200_ERR_NO_DEVICE = 3,   /* no sm_100 device: the library refuses to run */
+  ECDNA_B200_ERR_ALLOC = 4
+};
+
+/* sosa reaction order, main.rs:140-145; live variants of EcDNAEvent, process.rs:20-29 */
+enum {
+  ECDNA_B200_EV_BIRTH_NMINUS = 0, ECDNA_B200_EV_BIRTH_NPLUS = 1,
+  ECDNA_B200_EV_DEATH_NMINUS = 2, ECDNA_B200_EV_DEATH_NPLUS = 3
+};
+
+/* --segregation, src/clap_app.rs:232-238 (same order as SegregationOptions) */
+enum {
+  ECDNA_B200_SEG_DETERMINISTIC = 0, ECDNA_B200_SEG_BINOMIAL_NO_UNEVEN = 1,
+  ECDNA_B200_SEG_BINOMIAL = 2, ECDNA_B200_SEG_BINOMIAL_NO_NMINUS = 3
+};
+
+/* per-run stop reason: sosa::StopReason as printed at main.rs:205-210, plus the conditions the
+   reference turns into a panic (reported per run so one bad replicate does not kill the batch) */
+enum {
+  ECDNA_B200_STOP_NO_INDIVIDUALS = 0,
+  ECDNA_B200_STOP_MAX_ITERS = 1,
+  ECDNA_B200_STOP_MAX_TIME = 2,
+  ECDNA_B200_STOP_MAX_CELLS = 3,
+  ECDNA_B200_STOP_ABSORBING = 4,      /* cells left but all propensities zero */
+  ECDNA_B200_STOP_COPY_OVERFLOW = 5,  /* k*2 overflows u16: src/proliferation.rs:63-67 panics */
+  ECDNA_B200_STOP_HIST_OVERFLOW = 6,  /* copy number beyond params.max_copies */
+  ECDNA_B200_STOP_REPLAY_END = 7,     /* replay stream exhausted before a stop rule fired */
+  ECDNA_B200_STOP_REPLAY_BAD = 8      /* replay record inconsistent with the population */
+};
+/* bit set in stop_reason when the final histogram did not fit hist_stride bins */
+#define ECDNA_B200_FLAG_HIST_TRUNCATED 0x100u
+/* bit set when the replicate's histogram left shared memory for the HBM arena */
+#define ECDNA_B200_FLAG_SPILLED 0x200u
+
+enum { ECDNA_B200_RNG_PHILOX = 0, ECDNA_B200_RNG_REPLAY = 1 };
+enum { ECDNA_B200_STATE_AUTO = 0, ECDNA_B200_STATE_SMEM = 1, ECDNA_B200_STATE_HBM = 2 };
+
+/* ecdna_b200_params_t.flags */
+#define ECDNA_B200_WANT_DIGEST 0x1u /* maintain the histogram hash and the per-event chain digest */
+
+/* one record of the replay stream: the decisions of one iteration of sosa::simulate, in the order
+   the reference takes them (waiting time, event, cell picked, first daughter). 12 bytes. */
+typedef struct {
+  float dt;       /* NextReaction.time, added to the clock at process.rs:184/336 */
+  uint16_t k;     /* copies of the cell removed at proliferation.rs:57 / 126-133, else 0 */
+  uint16_t k1;    /* first value returned by Segregate::ecdna_segregation (segregation.rs:75-84) */
+  uint8_t event;  /* ECDNA_B200_EV_* */
+  uint8_t pad[3];
+} ecdna_b200_replay_event_t;
+
+/* The run parameters: SimulationOptions (main.rs:28-44) flattened. */
+typedef struct {
+  uint32_t abi_version;  /* ECDNA_B200_ABI_VERSION */
+  float b0, b1, d0, d1;  /* main.rs:31-34; d0=d1=0 is the pure-birth process (clap_app.rs:165-200) */
+  uint32_t segregation;  /* ECDNA_B200_SEG_* */
+  uint64_t max_cells;    /* options.max_cells, clap_app.rs:208; must be < 2^32 */
+  uint64_t max_iter;     /* options.max_iter_time.iter (MAX_ITER, main.rs:23); must be < 2^32 */
+  float max_time;        /* options.max_iter_time.time, clap_app.rs:205 */
+  uint64_t seed;         /* --seed, clap_app.rs:63-64 */
+  uint32_t bd_count_mode; /* 0: max_cells counts cells (documented CLI meaning, clap_app.rs:59-61);
+                             1: counts sosa's population array, which process.rs:339-344 fills with
+                             [n-,n+,n-,n+] for the birth-death process */
+
+  /* initial distribution (clap_app.rs:177-192): sparse histogram, k == 0 is the ecDNA- count */
+  uint32_t n_init;
+  const uint16_t* init_k;
+  const uint64_t* init_c;
+
+  /* snapshot sizes (clap_app.rs:102-134), ascending; may be NULL/0 */
+  uint32_t n_snapshots;
+  const uint64_t* snapshot_cells;
+
+  /* optional per-run rates [n_runs][4] = b0,b1,d0,d1: the ABC prior draws (abc.md:44-52) */
+  const float* rates_per_run;
+
+  /* random source */
+  uint32_t rng_mode;                       /* ECDNA_B200_RNG_* */
+  const ecdna_b200_replay_event_t* replay; /* all runs' records, concatenated */
+  const uint64_t* replay_offsets;          /* [n_runs + 1] record offsets into `replay` */
+
+  /* dynamics (CHANGELOG.md:34-40): dyn_points samples at multiples of dyn_dt of Gillespie time */
+  uint32_t dyn_points;
+  float dyn_dt;
+
+  /* ABC epilogue (abc.md:38-55): distances to a target distribution and the accept flag */
+  uint32_t abc_enabled;
+  const uint64_t* abc_target_hist; /* dense, [0] = cells without ecDNA */
+  uint32_t abc_target_len;
+  float abc_thresholds[4];         /* ks(ecdna), rel. mean, rel. entropy, rel. frequency */
+
+  /* engine knobs (0 = default) */
+  uint32_t state_mode;  /* ECDNA_B200_STATE_* */
+  uint32_t tile_width;  /* lanes per replicate: 32 (a warp), 16 or 8 */
+  uint32_t smem_bins;   /* histogram bins per replicate held in shared memory (multiple of 32) */
+  uint32_t max_copies;  /* largest copy number the HBM arena holds (<= 65535) */
+  uint32_t hist_stride; /* bins per output histogram */
+  uint32_t flags;       /* ECDNA_B200_WANT_* */
+} ecdna_b200_params_t;
+
+/* Per-run outputs.  Every pointer is optional (NULL = not wanted) and caller-owned.
+   For ecdna_b200_run they are host pointers, for ecdna_b200_run_device device pointers. */
+typedef struct {
+  uint32_t* stop_reason; /* [n]  ECDNA_B200_STOP_* | ECDNA_B200_FLAG_* */
+  uint64_t* nminus;      /* [n]  final_state[0], main.rs:124-128 */
+  uint64_t* nplus;       /* [n]  final_state[1] */
+  float* time;           /* [n]  process.time */
+  uint64_t* n_events;    /* [n]  iterations of sosa::simulate */
+  uint32_t* kmax;        /* [n]  largest copy number that ever occurred */
+  float* mean;           /* [n]  summary statistics of the final distribution */
+  float* frequency;
+  float* entropy;
+  float* variance;
+  float* abc_distance;   /* [n][4] ks, rel.mean, rel.entropy, rel.frequency */
+  uint8_t* abc_accept;   /* [n] */
+  uint64_t* hash;        /* [n]  digest of the final histogram (WANT_DIGEST) */
+  uint64_t* chain;       /* [n]  chained digest of the state after every event (WANT_DIGEST) */
+  uint32_t* hist;        /* [n][hist_stride] final distribution, [0] = nminus */
+  uint32_t* snap_count;  /* [n]  snapshots taken */
+  uint64_t* snap_cells;  /* [n][n_snapshots] */
+  float* snap_time;      /* [n][n_snapshots] */
+  uint32_t* snap_hist;   /* [n][n_snapshots][hist_stride] */
+  uint32_t* dyn_count;   /* [n] */
+  float* dyn;            /* [n][dyn_points][5] nminus, nplus, mean, variance, entropy */
+  uint64_t* sum_k;       /* [n]  sum over ecDNA+ events of the live histogram width (roofline) */
+  uint32_t* n_div;       /* [n]  ecDNA+ divisions */
+  uint32_t* n_death;     /* [n]  ecDNA+ deaths */
+} ecdna_b200_results_t;
+
+/* what the last run on a context measured (CUDA events on the context's stream) */
+typedef struct {
+  float kernel_ms;         /* the SSA kernel alone */
+  float total_ms;          /* copies + kernel, host-buffer entry point only */
+  uint32_t kernel_launches;
+  uint32_t tile_width, smem_bins, grid_blocks, block_threads, blocks_per_sm;
+  uint64_t h2d_bytes, d2h_bytes;
+  uint64_t total_events;   /* sum of n_events */
+  uint64_t alg_bytes;      /* SURVEY 8(d) flat-histogram model summed over all events */
+  uint32_t n_spilled;      /* replicates that moved to the HBM arena */
+} ecdna_b200_timing_t;
+
+typedef struct ecdna_b200_ctx ecdna_b200_ctx;
+
+/* One context per process and GPU.  `device` is the CUDA ordinal. */
+int ecdna_b200_create(int device, ecdna_b200_ctx** out);
+void ecdna_b200_destroy(ecdna_b200_ctx* ctx);
+const char* ecdna_b200_last_error(const ecdna_b200_ctx* ctx);
+int ecdna_b200_abi_version(void);
+
+/* Replaces main.rs:55-211 for idx in [idx_begin, idx_begin + n_runs).  Host buffers in and out;
+   blocking; host<->device copies happen inside. */
+int ecdna_b200_run(ecdna_b200_ctx* ctx, const ecdna_b200_params_t* params, uint64_t idx_begin, uint64_t n_runs,
+                   const ecdna_b200_results_t* results);
+
+/* Same, but `results` (and params->rates_per_run, replay, replay_offsets, abc_target_hist when
+   given) are DEVICE pointers and the work is enqueued on `cuda_stream` (a cudaStream_t, NULL =
+   the context's own stream) without a final synchronisation. */
+int ecdna_b200_run_device(ecdna_b200_ctx* ctx, const ecdna_b200_params_t* params, uint64_t idx_begin,
+                          uint64_t n_runs, const ecdna_b200_results_t* results, void* cuda_stream);
+
+/* Waits for everything enqueued by the context and fills `t` from its CUDA events. */
+int ecdna_b200_get_timing(ecdna_b200_ctx* ctx, ecdna_b200_timing_t* t);
+
+/* ABC prior draws: rates[i] = {b0, U(lo1,hi1), U(lo_d0,hi_d0), U(lo_d1,hi_d1)} from
+   Philox keyed (seed, idx_begin + i); device kernel, host output. */
+int ecdna_b200_abc_draw_priors(ecdna_b200_ctx* ctx, uint64_t seed, uint64_t idx_begin, uint64_t n_runs, float b0,
+                               const float b1_range[2], const float d0_range[2], const float d1_range[2],
+                               float* rates_out /* [n_runs][4], host */);
+
+/* Compacts the accepted runs of the last ecdna_b200_run_device call: writes their indices
+   (relative to idx_begin) to `accepted_idx` (device, [n_runs]) and the count to *n_accepted (host). */
+int ecdna_b200_compact_accepted(ecdna_b200_ctx* ctx, const uint8_t* accept_dev, uint64_t n_runs,
+                                uint32_t* accepted_idx_dev, uint32_t* n_accepted, void* cuda_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

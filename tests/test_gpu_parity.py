@@ -1,0 +1,239 @@
+"""GPU parity: libecdna_b200.so (through its C ABI) against the CPU oracle, same seeded inputs.
+
+Integer results (stop reason, counts, event numbers, histograms, digests) and the f32 clock must be
+BIT-EXACT: the oracle's histogram/philox configuration is the specification of the kernel's native
+mode, and replay mode consumes the decision stream of the reference-layout (vector, ChaCha8) oracle.
+Summary statistics are f32 reductions whose summation order differs: tolerance 2e-5 relative.
+"""
+import numpy as np
+import pytest
+
+import oracle_binding as ob
+
+pytestmark = pytest.mark.gpu
+
+STAT_RTOL = 2e-5
+
+
+def oracle_opts(o, run_idx, state=ob.STATE_HIST, rng=ob.RNG_PHILOX, rates=None, **kw):
+    b0, b1, d0, d1 = rates if rates is not None else (o.b0, o.b1, o.d0, o.d1)
+    return ob.make_opts(b0=b0, b1=b1, d0=d0, d1=d1, segregation=o.segregation, state=state, rng=rng,
+                        max_cells=o.max_cells, max_iter=o.max_iter, max_time=float(o.years), seed=o.seed,
+                        run_idx=run_idx, initial=o.distribution, **kw)
+
+
+def assert_run_equal(res, i, ref, stride, digest=True):
+    assert int(res.stop[i]) == ref.stop_reason, f"run {i}: stop {res.stop[i]} vs {ref.stop_reason}"
+    assert int(res.n_events[i]) == ref.n_events
+    assert int(res.nminus[i]) == ref.nminus and int(res.nplus[i]) == ref.nplus
+    assert np.float32(res.time[i]).view(np.uint32) == np.float32(ref.time).view(np.uint32)
+    assert int(res.kmax[i]) == ref.kmax
+    np.testing.assert_array_equal(res.hist[i].astype(np.uint64), ref.hist[:stride])
+    if digest:
+        assert int(res.hash[i]) == ref.hash
+        assert int(res.chain[i]) == ref.chain
+        assert int(res.sum_k[i]) == ref.sum_k
+        assert int(res.n_div[i]) == ref.n_div and int(res.n_death[i]) == ref.n_death
+
+
+WANT = ("stop_reason", "nminus", "nplus", "time", "n_events", "kmax", "hist", "hash", "chain", "sum_k", "n_div",
+        "n_death", "mean", "frequency", "entropy", "variance")
+
+CASES = {
+    "neutral": dict(b0=1.0, b1=1.0, cells=20000),
+    "selection": dict(b0=1.0, b1=1.5, cells=20000),
+    "birth_death": dict(b0=1.0, b1=1.2, d0=0.3, d1=0.3, cells=10000),
+    "death_nplus_only": dict(b0=1.0, b1=1.1, d1=0.4, cells=5000),
+    "deterministic": dict(b0=1.0, b1=1.3, cells=5000, segregation="deterministic", initial={4: 3, 0: 2}),
+    "no_uneven": dict(b0=1.0, b1=1.0, cells=5000, segregation="binomial-no-uneven"),
+    "no_nminus": dict(b0=0.9, b1=1.0, cells=5000, segregation="binomial-no-nminus"),
+    "k50": dict(b0=1.0, b1=1.0, cells=20000, initial={50: 1}),
+    "multi_bin_initial": dict(b0=1.0, b1=1.2, d0=0.1, d1=0.2, cells=8000, initial={0: 10, 2: 5, 33: 4, 64: 1, 7: 9}),
+    "time_stop": dict(b0=1.0, b1=1.0, years=5),
+    "extinction": dict(b0=0.5, b1=0.5, d0=1.0, d1=1.0, cells=1000, initial={3: 20, 0: 10}),
+}
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_native_bit_exact(pkg, ctx, name):
+    """Native (Philox) mode reproduces the histogram oracle bit for bit, every replicate."""
+    o = pkg.SimulationOptions(runs=12, save_snapshots=False, **CASES[name])
+    res = ctx.run(o, want=WANT, digest=True)
+    for i in range(o.runs):
+        ref = ob.run(oracle_opts(o, o.idx_begin + i), hist_cap=512)
+        assert_run_equal(res, i, ref, 512)
+        m, f, e, v = ob.stats(ref.hist)
+        np.testing.assert_allclose([res.mean[i], res.frequency[i], res.entropy[i]], [m, f, e], rtol=STAT_RTOL, atol=1e-6)
+        np.testing.assert_allclose(res.variance[i], v, rtol=1e-4, atol=1e-4)
+    assert res.timing.kernel_launches == 1 and res.timing.total_events == int(res.n_events.sum())
+
+
+@pytest.mark.parametrize("tile_width", [8, 16])
+@pytest.mark.parametrize("name", ["selection", "birth_death", "k50", "no_uneven"])
+def test_tile_widths_agree(pkg, ctx, name, tile_width):
+    """Sub-warp tiles (several replicates per warp) give the same bits as one warp per replicate."""
+    o = pkg.SimulationOptions(runs=37, save_snapshots=False, **CASES[name])
+    a = ctx.run(o, want=WANT, digest=True)
+    b = ctx.run(o, want=WANT, digest=True, tile_width=tile_width)
+    for f in ("stop_reason", "nminus", "nplus", "n_events", "kmax", "hist", "hash", "chain", "sum_k"):
+        np.testing.assert_array_equal(getattr(a, f), getattr(b, f), err_msg=f)
+    np.testing.assert_array_equal(a.time.view(np.uint32), b.time.view(np.uint32))
+
+
+@pytest.mark.parametrize("mode", ["hbm", "spill"])
+@pytest.mark.parametrize("name", ["selection", "birth_death", "k50", "multi_bin_initial"])
+def test_hbm_state_bit_exact(pkg, ctx, name, mode):
+    """The HBM-resident histogram, and the shared->HBM migration, do not change a single bit."""
+    o = pkg.SimulationOptions(runs=10, save_snapshots=False, **CASES[name])
+    kw = dict(state_mode=pkg.STATE_HBM) if mode == "hbm" else dict(smem_bins=32)
+    res = ctx.run(o, want=WANT, digest=True, **kw)
+    for i in range(o.runs):
+        ref = ob.run(oracle_opts(o, o.idx_begin + i), hist_cap=512)
+        assert_run_equal(res, i, ref, 512)
+    if mode == "spill":
+        assert res.timing.n_spilled > 0 and np.any(res.stop_reason & pkg.FLAG_SPILLED)
+
+
+def _vector_trace(o, run_idx, rng):
+    opts = oracle_opts(o, run_idx, state=ob.STATE_VECTOR, rng=rng)
+    cap = int(o.max_cells) * 8
+    return ob.run(opts, hist_cap=512, trace_cap=cap)
+
+
+@pytest.mark.parametrize("rng", [ob.RNG_RAND, ob.RNG_PHILOX])
+@pytest.mark.parametrize("name", ["neutral", "selection", "birth_death", "no_nminus", "k50", "extinction"])
+def test_replay_bit_exact(pkg, ctx, name, rng):
+    """Replay mode: the decision stream of the reference-layout oracle (per-cell vector, swap-remove,
+    ChaCha8 + rand conversions, or Philox) drives the kernel to the same state after every event."""
+    o = pkg.SimulationOptions(runs=6, save_snapshots=False, **CASES[name])
+    traces, refs = [], []
+    for i in range(o.runs):
+        r = _vector_trace(o, o.idx_begin + i, rng)
+        assert r.trace_len == r.n_events == len(r.trace)
+        traces.append(r.trace)
+        refs.append(r)
+    offsets = np.zeros(o.runs + 1, dtype=np.uint64)
+    offsets[1:] = np.cumsum([len(t) for t in traces])
+    stream = np.concatenate(traces) if offsets[-1] else np.zeros(1, dtype=ob.REPLAY_DTYPE)
+    res = ctx.run(o, want=WANT, digest=True, replay=stream, replay_offsets=offsets)
+    for i, ref in enumerate(refs):
+        # the stream ends exactly where the reference's stop rule fires, so the stop reason matches too
+        assert_run_equal(res, i, ref, 512)
+        # and the histogram oracle replaying the same stream agrees as well
+        h = ob.run(oracle_opts(o, o.idx_begin + i, rng=ob.RNG_REPLAY, replay=traces[i]), hist_cap=512)
+        assert (h.hash, h.chain, h.n_events) == (ref.hash, ref.chain, ref.n_events)
+
+
+def test_replay_detects_inconsistency(pkg, ctx):
+    o = pkg.SimulationOptions(runs=1, cells=200, save_snapshots=False)
+    r = _vector_trace(o, o.idx_begin, ob.RNG_RAND)
+    bad = r.trace.copy()
+    j = int(np.nonzero(bad["event"] == ob.EV_BIRTH_NPLUS)[0][3])
+    bad["k"][j] = 400  # no such cell
+    offsets = np.array([0, len(bad)], dtype=np.uint64)
+    res = ctx.run(o, want=WANT, replay=bad, replay_offsets=offsets)
+    assert int(res.stop[0]) == pkg.STOP_REPLAY_BAD and int(res.n_events[0]) == j
+    short = r.trace[:50].copy()
+    res = ctx.run(o, want=WANT, replay=short, replay_offsets=np.array([0, 50], dtype=np.uint64))
+    assert int(res.stop[0]) == pkg.STOP_REPLAY_END and int(res.n_events[0]) == 50
+
+
+def test_snapshots_match_oracle(pkg, ctx):
+    """process.rs:122-145: snapshot capture against the pre-event population, front-pop quirk included."""
+    o = pkg.SimulationOptions(b0=1.0, b1=1.2, d0=0.2, d1=0.2, cells=3000, runs=8, initial={2: 40, 0: 11},
+                              snapshots=[1, 51, 60, 500, 1000, 3000])
+    want = WANT + ("snap_count", "snap_cells", "snap_time", "snap_hist")
+    res = ctx.run(o, want=want, digest=True)
+    for i in range(o.runs):
+        ref = ob.run(oracle_opts(o, o.idx_begin + i, snapshots=o.snapshots), hist_cap=512)
+        assert_run_equal(res, i, ref, 512)
+        assert int(res.snap_count[i]) == ref.n_snap_taken
+        n = ref.n_snap_taken
+        np.testing.assert_array_equal(res.snap_cells[i][:n], ref.snap_cells[:n])
+        np.testing.assert_array_equal(res.snap_time[i][:n].view(np.uint32), ref.snap_time[:n].view(np.uint32))
+        np.testing.assert_array_equal(res.snap_hist[i][:n].astype(np.uint64), ref.snap_hist[:n])
+
+
+def test_default_snapshots_pure_birth(pkg, ctx):
+    o = pkg.SimulationOptions(cells=2000, runs=5)  # 11 default sizes, clap_app.rs:121-134
+    assert o.snapshots == [1, 201, 401, 601, 801, 1001, 1201, 1401, 1601, 1801, 2000]
+    res = ctx.run(o, want=WANT + ("snap_count", "snap_cells", "snap_hist"))
+    # the last size equals max_cells: the run stops before an event sees it (the final save covers it)
+    assert np.all(res.snap_count == 10)
+    np.testing.assert_array_equal(res.snap_hist.sum(axis=2)[:, :10], res.snap_cells[:, :10])
+
+
+def test_dynamics_match_oracle(pkg, ctx):
+    o = pkg.SimulationOptions(b0=1.0, b1=1.2, d0=0.3, d1=0.3, cells=5000, runs=6, save_snapshots=False)
+    res = ctx.run(o, want=WANT + ("dyn", "dyn_count"), dyn_points=300, dyn_dt=0.1)
+    for i in range(o.runs):
+        ref = ob.run(oracle_opts(o, o.idx_begin + i, dyn_points=300, dyn_dt=0.1), hist_cap=512)
+        assert int(res.dyn_count[i]) == ref.dyn_count
+        n = ref.dyn_count
+        np.testing.assert_array_equal(res.dyn[i][:n, :2], ref.dyn[:n, :2])
+        np.testing.assert_allclose(res.dyn[i][:n, 2:], ref.dyn[:n, 2:], rtol=1e-4, atol=1e-4)
+
+
+def test_abc_epilogue_matches_oracle(pkg, ctx):
+    """abc.md:38-55: per-draw distances to the target distribution, fused into the kernel's tail."""
+    n = 64
+    o = pkg.SimulationOptions(b0=1.0, b1=1.4, d0=0.2, d1=0.2, cells=3000, runs=n, save_snapshots=False)
+    target = ob.run(oracle_opts(o, 260), hist_cap=512).hist
+    rates = ctx.abc_draw_priors(seed=26, idx_begin=o.idx_begin, n_runs=n)
+    assert np.all(rates[:, 0] == 1.0) and np.all((rates[:, 1] >= 1.0) & (rates[:, 1] <= 2.0))
+    thr = (0.2, 0.5, 0.5, 0.5)
+    res = ctx.run(o, want=WANT + ("abc_distance", "abc_accept"), rates_per_run=rates, abc_target=target,
+                  abc_thresholds=thr, digest=True)
+    tm, tf, te, _ = ob.stats(target)
+    n_acc = 0
+    for i in range(n):
+        ref = ob.run(oracle_opts(o, o.idx_begin + i, rates=rates[i]), hist_cap=512)
+        assert_run_equal(res, i, ref, 512)
+        m, f, e, _ = ob.stats(ref.hist)
+        want = [ob.ks_distance(ref.hist, target), abs(m - tm) / tm, abs(e - te) / te, abs(f - tf) / tf]
+        np.testing.assert_allclose(res.abc_distance[i], want, rtol=1e-4, atol=1e-5)
+        margin = min(abs(w - t) for w, t in zip(want, thr))
+        if margin > 1e-4:
+            assert bool(res.abc_accept[i]) == all(w <= t for w, t in zip(want, thr))
+        n_acc += int(res.abc_accept[i])
+    assert 0 < n_acc < n
+
+
+def test_full_size_properties(pkg, ctx):
+    """BASELINE config 1 at full size (1e5 cells, 100 replicates): size-independent invariants."""
+    o = pkg.SimulationOptions(cells=100000, runs=100, save_snapshots=False)
+    res = ctx.run(o, want=WANT, digest=True)
+    assert np.all(res.stop == pkg.STOP_MAX_CELLS)
+    assert np.all(res.n_events == 99999)  # pure birth: one cell per event
+    assert np.all(res.nminus + res.nplus == 100000)
+    np.testing.assert_array_equal(res.hist.sum(axis=1), 100000)
+    np.testing.assert_array_equal(res.hist[:, 0], res.nminus)
+    # digest of the final histogram recomputed from the histogram itself
+    w = np.array([ob.lib().orc_hist_weight(k) for k in range(512)], dtype=np.uint64)
+    with np.errstate(over="ignore"):
+        h = (res.hist[:, 1:].astype(np.uint64) * w[None, 1:]).sum(axis=1, dtype=np.uint64)
+    np.testing.assert_array_equal(h, res.hash)
+    # neutral model: total copies per cell is a martingale with mean 1
+    assert abs(res.mean.mean() - 1.0) < 4 * res.mean.std() / 10
+    # three replicates checked bit for bit against the oracle
+    for i in (0, 57, 99):
+        assert_run_equal(res, i, ob.run(oracle_opts(o, o.idx_begin + i), hist_cap=512), 512)
+
+
+def test_copy_overflow_is_reported_not_fatal(pkg, ctx):
+    """k >= 32768 cannot double in u16: the reference panics (proliferation.rs:63-67); here the
+    replicate stops with COPY_OVERFLOW and the batch goes on."""
+    o = pkg.SimulationOptions(cells=50, runs=4, initial={40000: 1}, segregation="deterministic", save_snapshots=False)
+    res = ctx.run(o, want=WANT, state_mode=pkg.STATE_HBM, hist_stride=64)
+    assert np.all(res.stop == pkg.STOP_COPY_OVERFLOW)
+    ref = ob.run(oracle_opts(o, o.idx_begin), hist_cap=64)
+    assert ref.stop_reason == ob.STOP_COPY_OVERFLOW
+
+
+def test_bad_params_are_errors(pkg, ctx):
+    with pytest.raises(pkg.EcdnaB200Error):
+        ctx.run(pkg.SimulationOptions(b1=-1.0, runs=1, save_snapshots=False))
+    with pytest.raises(pkg.EcdnaB200Error):
+        ctx.run(pkg.SimulationOptions(runs=1, initial={0: 0}, save_snapshots=False))
+    with pytest.raises(pkg.EcdnaB200Error):
+        ctx.run(pkg.SimulationOptions(runs=1, save_snapshots=False), tile_width=4)
