@@ -1,0 +1,380 @@
+#!/usr/bin/env python
+"""bench.py -- SSA events/sec (and ABC sims/sec) of the B200 backend, one rank per GPU.
+
+A "step" is one pass of the hot path over one batch of replicates: BASELINE.json configs[1]
+(b1=1.5, grow 1 cell with 1 copy to 1e6 cells, 1e4 replicates, final ecDNA distribution +
+mean/frequency/entropy).  Every step simulates a different index range, so nothing is reused.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            # this framework
+  python bench.py --impl reference [--gpus N] --steps K --warmup W   # CPU restatement, all host cores
+
+Under torchrun (N>1) every rank runs its own replicate range (weak scaling, no data-path
+collective); ABC accepted draws are all-gathered over NCCL in the ABC leg.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+WORKLOADS = {
+    # name: (SimulationOptions kwargs, replicates per GPU, description)
+    "C1": (dict(b0=1.0, b1=1.0, cells=100_000), 100, "neutral, 1e5 cells, 100 replicates"),
+    "C2": (dict(b0=1.0, b1=1.5, cells=1_000_000), 10_000, "b1=1.5, 1e6 cells, 1e4 replicates, final distribution + mean/frequency/entropy"),
+    "C3": (dict(b0=1.0, b1=1.2, d0=0.3, d1=0.3, cells=100_000), 10_000, "birth-death d0=d1=0.3 b1=1.2, 1e5 cells, 1e4 replicates, dynamics"),
+    "C5": (dict(b0=1.0, b1=1.0, cells=10_000_000, initial={50: 1}), 1_000, "neutral, k0=50, 1e7 cells, 1e3 replicates"),
+}
+WANT = ("stop_reason", "nminus", "nplus", "time", "n_events", "kmax", "mean", "frequency", "entropy", "variance",
+        "hist")
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
+    ap.add_argument("--replicates", type=int, default=0, help="replicates per GPU per step (0 = the config's)")
+    ap.add_argument("--tile-width", type=int, default=0)
+    ap.add_argument("--smem-bins", type=int, default=0)
+    ap.add_argument("--state", default="auto", choices=["auto", "smem", "hbm"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-abc", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    return ap.parse_args()
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu):
+        self.gpu, self.proc, self.lines = gpu, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_port(opts_kw, seconds, n_threads=0, seed=26, idx0=260):
+    """The CPU restatement of the reference (per-cell vector state, ChaCha8, ziggurat, BINV/BTPE),
+    replicates over all host threads with a dynamic queue (rayon par_iter, main.rs:221-224)."""
+    import _pkg
+    import oracle_binding as ob
+    m = _pkg.load()
+    o = m.SimulationOptions(save_snapshots=False, seed=seed, **opts_kw)
+    cores = n_threads or os.cpu_count() or 1
+    oo = ob.make_opts(b0=o.b0, b1=o.b1, d0=o.d0, d1=o.d1, segregation=o.segregation, state=ob.STATE_VECTOR,
+                      rng=ob.RNG_RAND, max_cells=o.max_cells, max_time=float(o.years), seed=o.seed,
+                      initial=o.distribution)
+    # calibrate with one replicate per thread, then size the sample for ~`seconds`
+    t0 = time.perf_counter()
+    r = ob.run_batch(oo, idx0, cores, cores)
+    t1 = time.perf_counter() - t0
+    n = int(max(cores, min(cores * 4096, cores * seconds / max(t1, 1e-3))))
+    t0 = time.perf_counter()
+    r = ob.run_batch(oo, idx0 + cores, n, cores)
+    dt = time.perf_counter() - t0
+    return {"events": int(r.total_events), "seconds": dt, "replicates": n, "cores": cores,
+            "events_per_sec": r.total_events / dt, "sims_per_sec": n / dt}
+
+
+def reference_arm(args, rank, world):
+    """--impl reference: the reference's CPU implementation of the path on all host cores.  The Rust
+    binary cannot be built in this image (no cargo, crates not vendored), so this times the
+    reference-layout C++ restatement (oracle/), each step a bounded sample of the same workload."""
+    if rank != 0:
+        return
+    import _pkg
+    import oracle_binding as ob
+    m = _pkg.load()
+    kw, reps, desc = WORKLOADS[args.workload]
+    cores = os.cpu_count() or 1
+    o = m.SimulationOptions(save_snapshots=False, **kw)
+    oo = ob.make_opts(b0=o.b0, b1=o.b1, d0=o.d0, d1=o.d1, segregation=o.segregation, state=ob.STATE_VECTOR,
+                      rng=ob.RNG_RAND, max_cells=o.max_cells, max_time=float(o.years), seed=o.seed,
+                      initial=o.distribution)
+    t0 = time.perf_counter()
+    ob.run_batch(oo, 100, cores, cores)  # calibration: one replicate per thread
+    t1 = max(time.perf_counter() - t0, 1e-3)
+    per_step = max(1.0, min(15.0, 100.0 / max(1, args.steps + args.warmup)))
+    n = int(max(cores, min(reps, cores * per_step / t1)))
+    for w in range(args.warmup):
+        ob.run_batch(oo, o.idx_begin + w * n, n, cores)
+    events, tot_t = 0, 0.0
+    for s in range(args.steps):
+        t0 = time.perf_counter()
+        r = ob.run_batch(oo, o.idx_begin + (args.warmup + s) * n, n, cores)
+        tot_t += time.perf_counter() - t0
+        events += int(r.total_events)
+    v = events / tot_t
+    sample = (f"{n} replicates of {args.workload} per step over {cores} host threads (reference-layout C++ "
+              "restatement: per-cell u16 vector, ChaCha8, ziggurat, BINV/BTPE; the Rust reference cannot be built here)")
+    line = {
+        "impl": "reference", "metric": "ssa_events_per_sec", "value": v, "unit": "events/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {desc}", "replicates_per_step": n},
+        "cpu_baseline": {"value": v, "unit": "events/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "events/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        reference_arm(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import _pkg
+    m = _pkg.load()
+    m.build()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: libecdna_b200.so has no CPU path")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    ctx = m.Context(local_rank)
+
+    kw, reps, desc = WORKLOADS[args.workload]
+    reps = args.replicates or reps
+    state_mode = {"auto": m.STATE_AUTO, "smem": m.STATE_SMEM, "hbm": m.STATE_HBM}[args.state]
+    opts = m.SimulationOptions(save_snapshots=False, runs=reps, **kw)
+    stride = 512
+    dyn = dict(dyn_points=300, dyn_dt=0.1) if args.workload == "C3" else {}
+    want = WANT + (("dyn", "dyn_count") if dyn else ())
+    knobs = dict(tile_width=args.tile_width, smem_bins=args.smem_bins, state_mode=state_mode, hist_stride=stride, **dyn)
+
+    res_struct, tensors = m.device_results(torch, reps, want + ("sum_k", "n_div", "n_death"),
+                                           dyn_points=dyn.get("dyn_points", 0), hist_stride=stride, device=dev)
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def step(i):
+        # every step and every rank simulates its own index range: idx = seed*10 + ...
+        idx0 = opts.idx_begin + (i * world + rank) * reps
+        flush.zero_()
+        ctx.run_device(opts, reps, idx0, res_struct, stream=stream, **knobs)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    events = 0
+    alg_bytes = 0
+    kernel_ms = []
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        step(args.warmup + i)
+        # per-launch kernel time from the library's own CUDA events on the launching stream
+        t = ctx.timing()
+        kernel_ms.append(t.kernel_ms)
+        events += t.total_events
+        alg_bytes += t.alg_bytes
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop()
+    last = ctx.timing()
+
+    tmax = torch.tensor([ms], dtype=torch.float64, device=dev)
+    tot = torch.tensor([float(events)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    ms_all, events_all = float(tmax.item()), float(tot.item())
+    value = events_all / (ms_all * 1e-3)
+
+    # ---- sanity of what was simulated (cheap, outside the timed region) ----
+    stops = tensors["stop_reason"].cpu().numpy() & 0xFF
+    cells = (tensors["nminus"] + tensors["nplus"]).cpu().numpy()
+    ok = bool(np.all(stops == m.STOP_MAX_CELLS) and np.all(cells == opts.max_cells)) if not opts.birth_death else True
+    kmax = int(tensors["kmax"].max().item())
+
+    # ---- end to end through the host-buffer C ABI call (what a reference-side FFI caller sees) ----
+    e2e = None
+    if not args.no_e2e:
+        e2e_steps = max(1, min(args.steps, 2))
+        ctx.run(opts, n_runs=reps, idx_begin=opts.idx_begin + 7_000_000 + rank * reps, want=want, **knobs)
+        barrier()
+        t0 = time.perf_counter()
+        ev2 = 0
+        h2d = d2h = 0
+        for i in range(e2e_steps):
+            r = ctx.run(opts, n_runs=reps, idx_begin=opts.idx_begin + (8_000_000 + i) * world * reps + rank * reps,
+                        want=want, **knobs)
+            ev2 += int(r.n_events.sum())  # host read of the step's result
+            h2d, d2h = r.timing.h2d_bytes, r.timing.d2h_bytes
+        barrier()
+        dt = time.perf_counter() - t0
+        t2 = torch.tensor([dt], dtype=torch.float64, device=dev)
+        n2 = torch.tensor([float(ev2)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+            dist.all_reduce(n2, op=dist.ReduceOp.SUM)
+        e2e = {"value": float(n2.item()) / float(t2.item()), "unit": "events/s", "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
+               "api": "ecdna_b200_run (host buffers; copies inside the timed region)"}
+
+    # ---- ABC leg: sims/s on a C4-shaped sample, accepted draws all-gathered over NCCL ----
+    abc = None
+    if not args.no_abc:
+        abc = abc_leg(m, ctx, torch, dist, dev, rank, world)
+
+    # ---- roofline of the dominant (only) kernel ----
+    peak, peak_src = measured_peak()
+    k_ms = float(np.mean(kernel_ms))
+    achieved = (alg_bytes / args.steps) / (k_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "peak_source": peak_src, "kernel": f"ssa_kernel<{last.tile_width},false>",
+                "kernel_ms_per_launch": k_ms, "alg_bytes_per_launch": alg_bytes / args.steps,
+                "alg_bytes_per_event": alg_bytes / max(events, 1),
+                "note": "SURVEY 8(d) flat-histogram bytes; the histogram lives in shared memory, so real HBM "
+                        "traffic is the result write only (see profiles/)"}
+
+    if rank == 0:
+        cpu = None
+        if not args.no_cpu_baseline and world == 1:
+            c = cpu_port(kw, args.cpu_seconds)
+            cpu = {"value": c["events_per_sec"], "unit": "events/s", "cores": c["cores"], "kind": "port",
+                   "sample": f"{c['replicates']} replicates of {args.workload} ({c['events']} events, "
+                             f"{c['seconds']:.1f} s) over {c['cores']} host threads; reference-layout C++ "
+                             "restatement (vector state, ChaCha8, ziggurat, BINV/BTPE)"}
+        line = {
+            "metric": "ssa_events_per_sec", "value": value, "unit": "events/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_all / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {desc}", "replicates_per_gpu_per_step": reps,
+                       "events_per_step": events_all / args.steps, "tile_width": last.tile_width,
+                       "smem_bins": last.smem_bins, "state": args.state, "grid_blocks": last.grid_blocks,
+                       "blocks_per_sm": last.blocks_per_sm, "kmax": kmax, "spilled": last.n_spilled,
+                       "l2": "256 MiB buffer rewritten before every step; each step simulates fresh replicate "
+                             "indices", "results_ok": ok},
+            "e2e": e2e, "gpu_launches": args.steps * last.kernel_launches, "clocks": clocks, "roofline": roofline,
+            "cpu_baseline": cpu, "abc": abc,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def abc_leg(m, ctx, torch, dist, dev, rank, world, draws=16384, cells=100_000):
+    """BASELINE config 4 shape: prior draws over (b1, d0, d1), birth-death runs to 1e5 cells,
+    distances + accept fused in the kernel epilogue; accepted (rates, distances) all-gathered."""
+    opts = m.SimulationOptions(b0=1.0, b1=1.4, d0=0.2, d1=0.2, cells=cells, runs=draws, save_snapshots=False)
+    # synthetic target: one run at the "true" parameters
+    tgt = ctx.run(opts, n_runs=1, idx_begin=260, want=("hist",), hist_stride=512).hist[0].astype(np.uint64)
+    idx0 = opts.idx_begin + rank * draws
+    rates = ctx.abc_draw_priors(seed=26, idx_begin=idx0, n_runs=draws)
+    rates_d = torch.from_numpy(rates).to(dev)
+    tgt_d = torch.from_numpy(tgt.astype(np.int64)).to(dev)
+    want = ("stop_reason", "n_events", "abc_distance", "abc_accept", "mean", "frequency", "entropy")
+    rs, t = m.device_results(torch, draws, want, device=dev)
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    kw = dict(rates_per_run=rates_d, abc_target=tgt_d, abc_thresholds=(0.05, 0.1, 0.1, 0.1))
+    ctx.run_device(opts, draws, idx0, rs, stream=stream, **kw)  # warm-up
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    ctx.run_device(opts, draws, idx0, rs, stream=stream, **kw)
+    # compaction + the one collective of the path
+    acc_idx = torch.empty(draws, dtype=torch.int32, device=dev)
+    n_acc = ctx.compact_accepted(t["abc_accept"].data_ptr(), draws, acc_idx.data_ptr(), stream=stream)
+    sel = acc_idx[:n_acc].long()
+    payload = torch.cat([rates_d[sel], t["abc_distance"][sel]], dim=1) if n_acc else torch.zeros((0, 8), device=dev)
+    total_acc = n_acc
+    if world > 1:
+        counts = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
+        dist.all_gather(counts, torch.tensor([n_acc], dtype=torch.int64, device=dev))
+        mx = int(max(c.item() for c in counts))
+        pad = torch.zeros((mx, 8), device=dev)
+        pad[:n_acc] = payload
+        gathered = [torch.empty_like(pad) for _ in range(world)]
+        dist.all_gather(gathered, pad)
+        total_acc = int(sum(c.item() for c in counts))
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1)
+    tm = ctx.timing()
+    tmax = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    ms = float(tmax.item())
+    return {"metric": "abc_sims_per_sec", "value": draws * world / (ms * 1e-3), "unit": "sims/s",
+            "draws_per_gpu": draws, "cells": cells, "accepted": total_acc, "ms": ms,
+            "events_per_sec": tm.total_events * world / (ms * 1e-3),
+            "workload": "C4 shape: b1~U(1,2), d0,d1~U(0,0.5), 1e5-cell birth-death runs, target = run at "
+                        "(1.4,0.2,0.2); sample of the 1e6-draw config"}
+
+
+if __name__ == "__main__":
+    main()

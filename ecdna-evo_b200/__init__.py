@@ -55,6 +55,7 @@ class ParamsT(C.Structure):
         ("abc_thresholds", C.c_float * 4),
         ("state_mode", C.c_uint32), ("tile_width", C.c_uint32), ("smem_bins", C.c_uint32),
         ("max_copies", C.c_uint32), ("hist_stride", C.c_uint32), ("flags", C.c_uint32),
+        ("spill_records", C.c_uint32),
     ]
 
 
@@ -254,7 +255,7 @@ class Context:
     def make_params(self, opts, n_runs, rates_per_run=None, replay=None, replay_offsets=None, dyn_points=0,
                     dyn_dt=0.1, abc_target=None, abc_thresholds=(0.05, 0.1, 0.1, 0.1), state_mode=STATE_AUTO,
                     tile_width=0, smem_bins=0, max_copies=0, hist_stride=0, digest=False, bd_count_mode=0,
-                    snapshots=True):
+                    snapshots=True, spill_records=0):
         keep = {}
         p = ParamsT()
         p.abi_version = ABI_VERSION
@@ -284,6 +285,7 @@ class Context:
         p.state_mode, p.tile_width, p.smem_bins = state_mode, tile_width, smem_bins
         p.max_copies, p.hist_stride = max_copies, hist_stride
         p.flags = WANT_DIGEST if digest else 0
+        p.spill_records = spill_records
         p._keep = keep
         return p
 

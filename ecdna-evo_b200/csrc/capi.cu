@@ -53,8 +53,9 @@ struct ecdna_b200_ctx {
   cudaEvent_t ev_begin = nullptr, ev_k0 = nullptr, ev_k1 = nullptr, ev_end = nullptr;
   bool have_total = false;
   std::string err;
-  DevBuf init_k, init_c, snap, rates, replay, replay_off, abc_cdf, arena, counters, scratch, cols[C_COUNT];
-  size_t arena_tiles = 0, arena_kcap = 0;
+  DevBuf init_k, init_c, snap, rates, replay, replay_off, abc_cdf, arena, counters, scratch, park_list, park_rec,
+      cols[C_COUNT];
+  size_t arena_words = 0, arena_kcap = 0;
   ecdna_b200_timing_t timing{};
 };
 
@@ -71,42 +72,74 @@ int fail(ecdna_b200_ctx* ctx, int code, const std::string& msg) {
       return fail(ctx, ECDNA_B200_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__)); \
   } while (0)
 
-template <int L, bool REPLAY>
-int launch_one(ecdna_b200_ctx* ctx, SsaArgs& a, cudaStream_t st, const ecdna_b200_params_t* p) {
-  auto kern = ssa_kernel<L, REPLAY>;
+// one launch of ssa_kernel<L, GLOBAL, REPLAY>; returns the grid used through *grid_out
+template <int L, bool GLOBAL, bool REPLAY>
+int launch_kernel(ecdna_b200_ctx* ctx, SsaArgs& a, cudaStream_t st, uint64_t max_items, uint32_t* grid_out,
+                  uint32_t* bps_out) {
+  auto kern = ssa_kernel<L, GLOBAL, REPLAY>;
+  const int warps = kBlockThreads / 32;
   const int tiles_per_block = kBlockThreads / L;
-  const size_t smem = (size_t)tiles_per_block * a.kcap_s * sizeof(uint32_t);
-  if (smem > 200 * 1024) return fail(ctx, ECDNA_B200_ERR_BAD_PARAMS, "smem_bins too large for one block");
+  const size_t smem = GLOBAL ? 0 : (size_t)warps * Tile<L, GLOBAL>::window_words(a.kcap_s) * sizeof(uint32_t);
+  if (smem > 220 * 1024) return fail(ctx, ECDNA_B200_ERR_BAD_PARAMS, "smem_bins too large for this tile width");
   CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int bps = 0;
   CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, kBlockThreads, smem));
   if (bps < 1) return fail(ctx, ECDNA_B200_ERR_BAD_PARAMS, "kernel does not fit on an SM");
-  const uint64_t need = ((uint64_t)a.n_runs + tiles_per_block - 1) / tiles_per_block;
+  if (GLOBAL && bps > 8) bps = 8;  // bounds the arena: one (32 + kcap_g)-word window per resident warp
+  const uint64_t need = (max_items + tiles_per_block - 1) / tiles_per_block;
   uint64_t grid = (uint64_t)ctx->sm_count * bps;
   if (need < grid) grid = need;
   if (grid == 0) grid = 1;
-  // HBM arena: one window of kcap_g bins per resident tile, kept zeroed between replicates
-  a.arena = nullptr;
-  if (p->state_mode != ECDNA_B200_STATE_SMEM) {
-    const size_t tiles = (size_t)ctx->sm_count * bps * tiles_per_block;
-    if (tiles * a.kcap_g > ctx->arena_tiles * ctx->arena_kcap || a.kcap_g != ctx->arena_kcap) {
-      CU(ctx->arena.ensure(tiles * a.kcap_g * sizeof(uint32_t)));
-      CU(cudaMemsetAsync(ctx->arena.p, 0, tiles * a.kcap_g * sizeof(uint32_t), st));
-      ctx->arena_tiles = tiles;
-      ctx->arena_kcap = a.kcap_g;
+  if (GLOBAL) {
+    const size_t words = (size_t)grid * warps * Tile<32, true>::window_words(a.kcap_g);
+    if (words > ctx->arena_words) {
+      CU(ctx->arena.ensure(words * sizeof(uint32_t)));
+      ctx->arena_words = words;
+      CU(cudaMemsetAsync(ctx->arena.p, 0, words * sizeof(uint32_t), st));
+    } else if (a.kcap_g != ctx->arena_kcap) {
+      CU(cudaMemsetAsync(ctx->arena.p, 0, ctx->arena_words * sizeof(uint32_t), st));
     }
+    ctx->arena_kcap = a.kcap_g;
     a.arena = (uint32_t*)ctx->arena.p;
   }
-  CU(cudaEventRecord(ctx->ev_k0, st));
   kern<<<(unsigned)grid, kBlockThreads, smem, st>>>(a);
   CU(cudaGetLastError());
+  *grid_out = (uint32_t)grid;
+  *bps_out = (uint32_t)bps;
+  return ECDNA_B200_OK;
+}
+
+// phase 1: histogram in shared memory, tiles of L lanes; phase 2: parked replicates, histogram in HBM
+template <int L, bool REPLAY>
+int launch_all(ecdna_b200_ctx* ctx, SsaArgs& a, cudaStream_t st, const ecdna_b200_params_t* p) {
+  uint32_t grid = 0, bps = 0;
+  ecdna_b200_timing_t& tm = ctx->timing;
+  CU(cudaEventRecord(ctx->ev_k0, st));
+  if (p->state_mode == ECDNA_B200_STATE_HBM) {
+    a.park_list = nullptr;
+    a.allow_park = 0;
+    int rc = launch_kernel<32, true, REPLAY>(ctx, a, st, a.n_runs, &grid, &bps);
+    if (rc) return rc;
+    tm.kernel_launches = 1;
+    tm.tile_width = 32;
+  } else {
+    a.allow_park = p->state_mode == ECDNA_B200_STATE_AUTO ? 1u : 0u;
+    int rc = launch_kernel<L, false, REPLAY>(ctx, a, st, a.n_runs, &grid, &bps);
+    if (rc) return rc;
+    tm.kernel_launches = 1;
+    tm.tile_width = L;
+    if (a.allow_park) {
+      uint32_t g2 = 0, b2 = 0;
+      rc = launch_kernel<32, true, REPLAY>(ctx, a, st, a.n_runs, &g2, &b2);
+      if (rc) return rc;
+      tm.kernel_launches = 2;
+    }
+  }
   CU(cudaEventRecord(ctx->ev_k1, st));
-  ctx->timing.kernel_launches = 1;
-  ctx->timing.tile_width = L;
-  ctx->timing.smem_bins = a.kcap_s;
-  ctx->timing.grid_blocks = (uint32_t)grid;
-  ctx->timing.block_threads = kBlockThreads;
-  ctx->timing.blocks_per_sm = (uint32_t)bps;
+  tm.smem_bins = a.kcap_s;
+  tm.grid_blocks = grid;
+  tm.block_threads = kBlockThreads;
+  tm.blocks_per_sm = bps;
   return ECDNA_B200_OK;
 }
 
@@ -190,7 +223,7 @@ int validate(ecdna_b200_ctx* ctx, const ecdna_b200_params_t* p, uint64_t n_runs)
   if (p->rng_mode > 1) return fail(ctx, ECDNA_B200_ERR_BAD_PARAMS, "unknown rng_mode");
   if (p->rng_mode == ECDNA_B200_RNG_REPLAY && (!p->replay || !p->replay_offsets)) return fail(ctx, ECDNA_B200_ERR_BAD_PARAMS, "replay mode needs replay and replay_offsets");
   if (p->state_mode > 2) return fail(ctx, ECDNA_B200_ERR_BAD_PARAMS, "unknown state_mode");
-  if (p->tile_width != 0 && p->tile_width != 8 && p->tile_width != 16 && p->tile_width != 32) return fail(ctx, ECDNA_B200_ERR_BAD_PARAMS, "tile_width must be 8, 16 or 32");
+  if (p->tile_width != 0 && p->tile_width != 4 && p->tile_width != 8 && p->tile_width != 16 && p->tile_width != 32) return fail(ctx, ECDNA_B200_ERR_BAD_PARAMS, "tile_width must be 4, 8, 16 or 32");
   if (p->max_copies > 65535) return fail(ctx, ECDNA_B200_ERR_BAD_PARAMS, "max_copies must be <= 65535 (DNACopy is u16)");
   if (p->abc_enabled && (!p->abc_target_hist || p->abc_target_len == 0)) return fail(ctx, ECDNA_B200_ERR_BAD_PARAMS, "abc_enabled needs a target distribution");
   if (p->dyn_points && !(p->dyn_dt > 0.f)) return fail(ctx, ECDNA_B200_ERR_BAD_PARAMS, "dyn_dt must be > 0");
@@ -216,13 +249,13 @@ int run_common(ecdna_b200_ctx* ctx, const ecdna_b200_params_t* p, uint64_t idx_b
   a.max_iter_m1 = (uint32_t)(p->max_iter - 1);
   a.max_time = p->max_time;
   a.seed_lo = (uint32_t)p->seed; a.seed_hi = (uint32_t)(p->seed >> 32);
+  for (uint32_t r = 0; r < 10; ++r) { a.pk[2 * r] = a.seed_lo + r * 0x9E3779B9u; a.pk[2 * r + 1] = a.seed_hi + r * 0xBB67AE85u; }
   a.idx_begin = idx_begin;
   a.n_runs = (uint32_t)n_runs;
   a.dyn_points = p->dyn_points; a.dyn_dt = p->dyn_dt;
-  a.state_mode = p->state_mode;
   a.flags = p->flags;
-  a.kcap_s = p->smem_bins ? ((p->smem_bins + 31u) & ~31u) : 512u;
-  a.kcap_g = ((p->max_copies ? p->max_copies : 65535u) + 32u) & ~31u;
+  a.kcap_s = p->smem_bins ? ((p->smem_bins + 127u) & ~127u) : 512u;  // bins come in rows of 4 x 32
+  a.kcap_g = ((p->max_copies ? p->max_copies : 65535u) + 128u) & ~127u;
   if (a.kcap_g < a.kcap_s) a.kcap_g = a.kcap_s;
   a.hist_stride = p->hist_stride ? p->hist_stride : 512u;
   const uint32_t stride = a.hist_stride;
@@ -320,15 +353,26 @@ int run_common(ecdna_b200_ctx* ctx, const ecdna_b200_params_t* p, uint64_t idx_b
     }
   }
   a.out = dev;
-  CU(ctx->counters.ensure(64));
-  CU(cudaMemsetAsync(ctx->counters.p, 0, 64, st));
-  a.work_counter = (uint32_t*)ctx->counters.p;
-  a.totals = (unsigned long long*)((char*)ctx->counters.p + 8);
+  CU(ctx->counters.ensure(128));
+  CU(cudaMemsetAsync(ctx->counters.p, 0, 128, st));
+  a.work_counter = (uint32_t*)ctx->counters.p;                              // [0], [1]: the two queues
+  a.park_count = (uint32_t*)ctx->counters.p + 2;
+  a.totals = (unsigned long long*)((char*)ctx->counters.p + 16);
+  if (p->state_mode == ECDNA_B200_STATE_AUTO) {
+    uint64_t cap = p->spill_records == 0xFFFFFFFFu ? 0 : (p->spill_records ? p->spill_records : 32768u);
+    if (cap > n_runs) cap = n_runs;
+    CU(ctx->park_list.ensure(n_runs * 4));
+    CU(ctx->park_rec.ensure((cap ? cap : 1) * (size_t)(kParkHdr + 32u + a.kcap_s) * 4));
+    a.park_list = (uint32_t*)ctx->park_list.p;
+    a.park_rec = (uint32_t*)ctx->park_rec.p;
+    a.park_cap = (uint32_t)cap;
+  }
 
   const uint32_t L = p->tile_width ? p->tile_width : 32u;
-  if (L == 32) rc = replay ? launch_one<32, true>(ctx, a, st, p) : launch_one<32, false>(ctx, a, st, p);
-  else if (L == 16) rc = replay ? launch_one<16, true>(ctx, a, st, p) : launch_one<16, false>(ctx, a, st, p);
-  else rc = replay ? launch_one<8, true>(ctx, a, st, p) : launch_one<8, false>(ctx, a, st, p);
+  if (L == 32) rc = replay ? launch_all<32, true>(ctx, a, st, p) : launch_all<32, false>(ctx, a, st, p);
+  else if (L == 16) rc = replay ? launch_all<16, true>(ctx, a, st, p) : launch_all<16, false>(ctx, a, st, p);
+  else if (L == 8) rc = replay ? launch_all<8, true>(ctx, a, st, p) : launch_all<8, false>(ctx, a, st, p);
+  else rc = replay ? launch_all<4, true>(ctx, a, st, p) : launch_all<4, false>(ctx, a, st, p);
   if (rc) return rc;
 
   if (!device_io) {
@@ -444,7 +488,7 @@ void ecdna_b200_destroy(ecdna_b200_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   DevBuf* bufs[] = {&ctx->init_k, &ctx->init_c, &ctx->snap, &ctx->rates, &ctx->replay, &ctx->replay_off,
-                    &ctx->abc_cdf, &ctx->arena, &ctx->counters, &ctx->scratch};
+                    &ctx->abc_cdf, &ctx->arena, &ctx->counters, &ctx->scratch, &ctx->park_list, &ctx->park_rec};
   for (DevBuf* b : bufs) b->release();
   for (auto& b : ctx->cols) b.release();
   cudaEventDestroy(ctx->ev_begin); cudaEventDestroy(ctx->ev_k0); cudaEventDestroy(ctx->ev_k1); cudaEventDestroy(ctx->ev_end);
@@ -476,7 +520,7 @@ int ecdna_b200_get_timing(ecdna_b200_ctx* ctx, ecdna_b200_timing_t* t) {
     CU(cudaEventElapsedTime(&ctx->timing.total_ms, ctx->ev_begin, ctx->ev_end));
   }
   unsigned long long tot[5];
-  CU(cudaMemcpy(tot, (char*)ctx->counters.p + 8, sizeof tot, cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(tot, (char*)ctx->counters.p + 16, sizeof tot, cudaMemcpyDeviceToHost));
   ctx->timing.total_events = tot[0];
   // division = 4K + 24 + 16, death = 4K + 8 + 16, ecDNA- event = 16 bytes
   ctx->timing.alg_bytes = 4ull * tot[1] + 24ull * tot[2] + 8ull * tot[3] + 16ull * tot[0];

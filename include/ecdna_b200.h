@@ -120,11 +120,13 @@ typedef struct {
 
   /* engine knobs (0 = default) */
   uint32_t state_mode;  /* ECDNA_B200_STATE_* */
-  uint32_t tile_width;  /* lanes per replicate: 32 (a warp), 16 or 8 */
+  uint32_t tile_width;  /* lanes per replicate: 32 (a warp), 16, 8 or 4 */
   uint32_t smem_bins;   /* histogram bins per replicate held in shared memory (multiple of 32) */
   uint32_t max_copies;  /* largest copy number the HBM arena holds (<= 65535) */
   uint32_t hist_stride; /* bins per output histogram */
   uint32_t flags;       /* ECDNA_B200_WANT_* */
+  uint32_t spill_records; /* parked replicates whose state is saved for the HBM launch (others restart);
+                             0 = default (32768), 0xFFFFFFFF = none */
 } ecdna_b200_params_t;
 
 /* Per-run outputs.  Every pointer is optional (NULL = not wanted) and caller-owned.
@@ -160,7 +162,7 @@ typedef struct {
 typedef struct {
   float kernel_ms;         /* the SSA kernel alone */
   float total_ms;          /* copies + kernel, host-buffer entry point only */
-  uint32_t kernel_launches;
+  uint32_t kernel_launches; /* 1, or 2 when the HBM launch for parked replicates was enqueued */
   uint32_t tile_width, smem_bins, grid_blocks, block_threads, blocks_per_sm;
   uint64_t h2d_bytes, d2h_bytes;
   uint64_t total_events;   /* sum of n_events */

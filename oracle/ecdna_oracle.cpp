@@ -308,13 +308,14 @@ struct PhiloxSource {  // rng 1: every draw is a pure function of (seed, run, ev
     }
     return std::isinf(lambda) ? 0.0f : F_INF;
   }
-  // slots 4+2j (high word) and 5+2j (low word), word 0: Lemire's unbiased bounded integer
+  // Lemire's unbiased bounded integer from a 64-bit uniform: first draw = word 1 of slot 0 (high)
+  // and of slot 1 (low); the rare redraw j >= 1 takes word 0 of slots 4+2j (high) and 5+2j (low)
   uint64_t pick(uint64_t n) {
     for (uint32_t j = 0;; ++j) {
       uint32_t a[4], b[4];
-      philox_slot(key, ev, 4 + 2 * j, a);
-      philox_slot(key, ev, 5 + 2 * j, b);
-      const uint64_t x = ((uint64_t)a[0] << 32) | b[0];
+      philox_slot(key, ev, j == 0 ? 0u : 4 + 2 * j, a);
+      philox_slot(key, ev, j == 0 ? 1u : 5 + 2 * j, b);
+      const uint64_t x = j == 0 ? (((uint64_t)a[1] << 32) | b[1]) : (((uint64_t)a[0] << 32) | b[0]);
       const unsigned __int128 m = (unsigned __int128)x * n;
       const uint64_t lo = (uint64_t)m;
       if (lo >= n || j >= 13) return (uint64_t)(m >> 64);
@@ -323,14 +324,14 @@ struct PhiloxSource {  // rng 1: every draw is a pure function of (seed, run, ev
     }
   }
   // Binomial(n, 1/2) = popcount of n independent fair bits: bit b lives in slot
-  // attempt*1024 + b/96, word 1 + (b%96)/32, bit b%32.  Exact, integer only.
+  // attempt*1024 + b/64, word 2 + (b%64)/32, bit b%32.  Exact, integer only.
   uint64_t binomial_half(uint64_t n, uint32_t attempt) {
     uint64_t count = 0;
     uint32_t slot = attempt * 1024u;
     for (uint64_t left = n; left > 0; ++slot) {
       uint32_t x[4];
       philox_slot(key, ev, slot, x);
-      for (int w = 1; w <= 3 && left > 0; ++w) {
+      for (int w = 2; w <= 3 && left > 0; ++w) {
         const uint32_t take = left >= 32 ? 32u : (uint32_t)left;
         const uint32_t mask = take == 32 ? 0xFFFFFFFFu : ((1u << take) - 1u);
         count += (uint64_t)__builtin_popcount(x[w] & mask);

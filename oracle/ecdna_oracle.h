@@ -28,7 +28,7 @@
  *   rng 0 "rand"    ChaCha8(seed).set_stream(idx) (main.rs:57-58) with rand-0.8
  *                   conversions, ziggurat Exp1, BINV/BTPE binomial [RECALL]
  *   rng 1 "philox"  Philox4x32-10, key=(seed), counter=(event, slot, run): the
- *                   GPU's native stream; exponentials by a deterministic f32 log,
+ *                   GPU's native stream (slot layout in ecdna_oracle.cpp PhiloxSource); exponentials by a deterministic f32 log,
  *                   Binomial(2k,1/2) as the popcount of 2k random bits (exact)
  *   rng 2 "replay"  consumes a decision stream {event, dt, k, k1} (histogram state
  *                   only); the stream is what either state emits as trace_out.

@@ -65,10 +65,10 @@ def test_deterministic_log_accuracy_and_edges():
         assert got > 0 and abs(got - want) <= 2.5e-7 * max(want, 1e-3) + 1e-9, (m, got, want)
 
 
-@pytest.mark.parametrize("k", [1, 2, 5, 9, 10, 11, 47, 48, 49, 500, 1536, 1537, 5000, 32767])
+@pytest.mark.parametrize("k", [1, 2, 5, 9, 10, 11, 31, 32, 33, 128, 129, 500, 1024, 1025, 5000, 32767])
 def test_popcount_binomial_matches_exact_pmf(k):
     """Philox segregation draw: chi-square against Binomial(2k, 1/2), incl. the slot boundaries
-    (96 bits per slot, 3072 per 32 slots)."""
+    (64 bits per slot)."""
     n = 2 * k
     N = 20000
     draws = np.array([ob.lib().orc_binomial_half_philox(7, 3, e, 0, n) for e in range(N)])
@@ -123,7 +123,7 @@ def test_pick_is_uniform(n):
     b = np.array([ob.lib().orc_pick_philox(1, 2, e, n) for e in range(N)], dtype=np.uint64)
     for x in (a, b):
         assert x.max() < n
-        if n <= 7:
+        if 1 < n <= 7:
             obs = np.bincount(x.astype(np.int64), minlength=n)
             assert sps.chisquare(obs).pvalue > 1e-4
         elif n > 1000:
