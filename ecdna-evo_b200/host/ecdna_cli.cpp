@@ -1,0 +1,403 @@
+// ecdna -- host front end over libecdna_b200.so with the reference's command line and output files.
+//
+// Mirrors, flag for flag, the clap definition of the reference (src/clap_app.rs:26-100) and the
+// defaults that Cli::build derives (clap_app.rs:136-230); replaces the rayon loop over replicate
+// indices (src/main.rs:212-225) by one call of ecdna_b200_run(); writes the same files as `save`
+// (src/process.rs:31-55) with the names of src/lib.rs:27-45: one JSON histogram per triggered
+// snapshot, one for the final state, one per --subsamples size.
+//
+// The reference is Rust; no Rust toolchain exists in this image, so the host side above the C ABI is
+// C++ (INTEGRATION.md shows the Rust binding a maintainer would add instead of this file).
+#include <sys/stat.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <ctime>
+#include <fstream>
+#include <map>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include "ecdna_b200.h"
+
+namespace {
+
+constexpr uint64_t kMaxIter = 1000000000ull;   // main.rs:23
+constexpr uint64_t kMaxCells = 1000000000ull;  // main.rs:25
+
+struct Cli {
+  std::string segregation = "binomial";  // clap_app.rs:35-36
+  std::string growth = "exponential";    // clap_app.rs:38-39
+  float b0 = 1.f, b1 = 1.f;              // clap_app.rs:41-45
+  bool has_d0 = false, has_d1 = false;
+  float d0 = 0.f, d1 = 0.f;              // clap_app.rs:49-55
+  bool has_years = false, has_cells = false;
+  uint64_t years = 0, cells = 0;         // clap_app.rs:57-61
+  uint64_t seed = 26;                    // clap_app.rs:63-64
+  bool debug = false, sequential = false;
+  std::string path, initial;
+  uint64_t runs = 12;                    // clap_app.rs:89-91
+  bool has_subsamples = false, has_snapshots = false;
+  std::vector<uint64_t> subsamples, snapshots;
+  int verbosity = 0;
+  // engine knobs (not in the reference)
+  int device = 0;
+  uint32_t tile_width = 0, state_mode = 0;
+};
+
+[[noreturn]] void die(const std::string& msg) {
+  std::fprintf(stderr, "error: %s\n\nFor more information, try '--help'.\n", msg.c_str());
+  std::exit(2);
+}
+
+void usage() {
+  std::puts(
+      "Study the effect of the random segregation and positive selection on the ecDNA dynamics using a\n"
+      "stochastic simulation algorithm (SSA) aka Gillespie algorithm  [B200 backend]\n\n"
+      "Usage: ecdna [OPTIONS] <DIR>\n\n"
+      "Arguments:\n  <DIR>  Path to store the results of the simulations\n\n"
+      "Options:\n"
+      "      --segregation <SEGREGATION>  [default: binomial] [possible values: deterministic,\n"
+      "                                   binomial-no-uneven, binomial, binomial-no-nminus]\n"
+      "      --growth <GROWTH>            [default: exponential] [possible values: exponential, constant]\n"
+      "      --b0 <RATE>                  Proliferation rate of the cells without ecDNAs [default: 1]\n"
+      "      --b1 <RATE>                  Proliferation rate of the cells with ecDNAs [default: 1]\n"
+      "      --d0 <RATE>                  Death rate of the cells without ecDNAs\n"
+      "      --d1 <RATE>                  Death rate of the cells with ecDNAs\n"
+      "  -y, --years <YEARS>              Number of years to simulate before stopping\n"
+      "  -c, --cells <CELLS>              Number of cells to simulate before stopping\n"
+      "      --seed <SEED>                Seed for reproducibility [default: 26]\n"
+      "  -d, --debug                      max verbosity, 1 sequential simulation\n"
+      "  -s, --sequential                 accepted for compatibility (replicates always run on the GPU)\n"
+      "      --initial <FILE>             The JSON file used as an initial starting distribution\n"
+      "  -r, --runs <RUNS>                Number of independent realisations [default: 12]\n"
+      "      --subsamples[=<N>...]        Subsample the ecDNA distribution at the end of the simulation\n"
+      "      --snapshots[=<N>...]         Number of cells that will trigger the saving of the distribution\n"
+      "  -v, --verbosity...\n"
+      "      --device <N>  --tile-width <4|8|16|32>  --state <auto|smem|hbm>   (B200 engine knobs)\n"
+      "  -h, --help\n  -V, --version");
+}
+
+std::vector<uint64_t> parse_list(const std::string& v) {
+  std::vector<uint64_t> out;
+  std::stringstream ss(v);
+  std::string tok;
+  while (std::getline(ss, tok, ',')) {
+    if (tok.empty()) continue;
+    char* end = nullptr;
+    const unsigned long long x = std::strtoull(tok.c_str(), &end, 10);
+    if (*end) die("invalid value '" + tok + "': invalid digit found in string");
+    out.push_back(x);
+  }
+  return out;
+}
+
+Cli parse(int argc, char** argv) {
+  Cli c;
+  bool have_path = false, runs_given = false, verb_given = false;
+  auto need = [&](int& i, const std::string& name) -> std::string {
+    if (i + 1 >= argc) die("a value is required for '" + name + "' but none was supplied");
+    return argv[++i];
+  };
+  for (int i = 1; i < argc; ++i) {
+    std::string a = argv[i], val;
+    const size_t eq = a.find('=');
+    bool has_eq = false;
+    if (a.rfind("--", 0) == 0 && eq != std::string::npos) { val = a.substr(eq + 1); a = a.substr(0, eq); has_eq = true; }
+    auto value = [&]() { return has_eq ? val : need(i, a); };
+    if (a == "-h" || a == "--help") { usage(); std::exit(0); }
+    else if (a == "-V" || a == "--version") { std::puts("Dynamics 0.26.0-b200"); std::exit(0); }
+    else if (a == "--segregation") c.segregation = value();
+    else if (a == "--growth") c.growth = value();
+    else if (a == "--b0") c.b0 = std::strtof(value().c_str(), nullptr);
+    else if (a == "--b1") c.b1 = std::strtof(value().c_str(), nullptr);
+    else if (a == "--d0") { c.d0 = std::strtof(value().c_str(), nullptr); c.has_d0 = true; }
+    else if (a == "--d1") { c.d1 = std::strtof(value().c_str(), nullptr); c.has_d1 = true; }
+    else if (a == "-y" || a == "--years") { c.years = std::strtoull(value().c_str(), nullptr, 10); c.has_years = true; }
+    else if (a == "-c" || a == "--cells") { c.cells = std::strtoull(value().c_str(), nullptr, 10); c.has_cells = true; }
+    else if (a == "--seed") c.seed = std::strtoull(value().c_str(), nullptr, 10);
+    else if (a == "-d" || a == "--debug") c.debug = true;
+    else if (a == "-s" || a == "--sequential") c.sequential = true;
+    else if (a == "--initial") c.initial = value();
+    else if (a == "-r" || a == "--runs") { c.runs = std::strtoull(value().c_str(), nullptr, 10); runs_given = true; }
+    else if (a == "--subsamples") { c.has_subsamples = true; if (has_eq) c.subsamples = parse_list(val); }  // require_equals
+    else if (a == "--snapshots") { c.has_snapshots = true; if (has_eq) c.snapshots = parse_list(val); }
+    else if (a == "--device") c.device = std::atoi(value().c_str());
+    else if (a == "--tile-width") c.tile_width = (uint32_t)std::atoi(value().c_str());
+    else if (a == "--state") {
+      const std::string s = value();
+      c.state_mode = s == "smem" ? ECDNA_B200_STATE_SMEM : (s == "hbm" ? ECDNA_B200_STATE_HBM : ECDNA_B200_STATE_AUTO);
+    }
+    else if (a.size() >= 2 && a[0] == '-' && a[1] == 'v') { c.verbosity += (int)a.size() - 1; verb_given = true; }
+    else if (a == "--verbosity") { c.verbosity += 1; verb_given = true; }
+    else if (!a.empty() && a[0] == '-') die("unexpected argument '" + a + "' found");
+    else if (!have_path) { c.path = a; have_path = true; }
+    else die("unexpected argument '" + a + "' found");
+  }
+  if (!have_path) die("the following required arguments were not provided:\n  <DIR>");
+  if (c.has_years && c.has_cells) die("the argument '--years <YEARS>' cannot be used with '--cells <CELLS>'");
+  if (c.debug && (c.has_years || c.has_cells || c.sequential || runs_given || verb_given))
+    die("the argument '--debug' cannot be used with one or more of the other specified arguments");
+  if (!c.initial.empty() && (c.initial.size() < 5 || c.initial.substr(c.initial.size() - 5) != ".json"))
+    die("invalid value '" + c.initial + "' for '--initial <FILE>': Must be JSON file: extension must be .json)");
+  return c;
+}
+
+// Rust's `f32::to_string`: shortest decimal that round-trips, never in exponent form
+std::string rust_f32_to_string(float v) {
+  if (std::isnan(v)) return "NaN";
+  if (std::isinf(v)) return v > 0 ? "inf" : "-inf";
+  if (v == 0.f) return std::signbit(v) ? "-0" : "0";
+  char buf[64];
+  int prec = 0;
+  for (; prec < 9; ++prec) {
+    std::snprintf(buf, sizeof buf, "%.*e", prec, (double)v);
+    if (std::strtof(buf, nullptr) == v) break;
+  }
+  std::string digits;
+  const char* p = buf;
+  bool neg = false;
+  if (*p == '-') { neg = true; ++p; }
+  for (; *p && *p != 'e'; ++p) if (*p != '.') digits.push_back(*p);
+  const int exp10 = std::atoi(p + 1);
+  while (digits.size() > 1 && digits.back() == '0') digits.pop_back();
+  std::string out;
+  const int point = exp10 + 1;  // digits before the decimal point
+  if (point <= 0) out = "0." + std::string((size_t)-point, '0') + digits;
+  else if ((size_t)point >= digits.size()) out = digits + std::string((size_t)point - digits.size(), '0');
+  else out = digits.substr(0, (size_t)point) + "." + digits.substr((size_t)point);
+  return neg ? "-" + out : out;
+}
+std::string dotted(float v) {
+  std::string s = rust_f32_to_string(v);
+  std::string out;
+  for (char ch : s) { if (ch == '.') out += "dot"; else out.push_back(ch); }
+  return out;
+}
+// lib.rs:27-45
+std::string make_filename(const Cli& c, bool birth_death, float d0, float d1, uint64_t idx) {
+  if (birth_death) return dotted(c.b0) + "b0_" + dotted(c.b1) + "b1_" + dotted(d0) + "d0_" + dotted(d1) + "d1_" + std::to_string(idx) + "idx";
+  return dotted(c.b0) + "b0_" + dotted(c.b1) + "b1_0d0_0d1_" + std::to_string(idx) + "idx";
+}
+
+void mkdirs(const std::string& path) {
+  std::string cur;
+  for (size_t i = 0; i <= path.size(); ++i) {
+    if (i == path.size() || path[i] == '/') {
+      if (!cur.empty()) ::mkdir(cur.c_str(), 0777);
+    }
+    if (i < path.size()) cur.push_back(path[i]);
+  }
+}
+
+// process.rs:31-55
+void save(const Cli& c, const std::string& filename, float time, const uint32_t* hist, uint32_t len, int verbosity) {
+  uint64_t cells = 0;
+  for (uint32_t k = 0; k < len; ++k) cells += hist[k];
+  char tbuf[64];
+  std::snprintf(tbuf, sizeof tbuf, "%.1f", (double)time);
+  std::string tp;
+  for (const char* p = tbuf; *p; ++p) { if (*p == '.') tp += "dot"; else tp.push_back(*p); }
+  tp += "years";
+  const std::string dir = c.path + "/" + std::to_string(cells) + "cells/ecdna/" + tp;
+  mkdirs(dir);
+  const std::string file = dir + "/" + filename + ".json";
+  if (verbosity > 0) std::printf("saving state at time %s with %llu cells in \"%s\"\n", rust_f32_to_string(time).c_str(), (unsigned long long)cells, file.c_str());
+  std::ofstream f(file);
+  if (!f) { std::fprintf(stderr, "Cannot create %s\n", file.c_str()); std::exit(101); }
+  f << "{";
+  bool first = true;
+  for (uint32_t k = 0; k < len; ++k) {
+    if (!hist[k]) continue;
+    if (!first) f << ",";
+    f << "\"" << k << "\":" << hist[k];
+    first = false;
+  }
+  f << "}";
+}
+
+// {"0": 2, "1": 2, "10": 1} (dynamics.md:7-8)
+std::map<uint32_t, uint64_t> load_json_hist(const std::string& path) {
+  std::ifstream f(path);
+  if (!f) die("Cannot load the ecDNA distribution from \"" + path + "\"");
+  std::string s((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+  std::map<uint32_t, uint64_t> out;
+  size_t i = 0;
+  while ((i = s.find('"', i)) != std::string::npos) {
+    const size_t j = s.find('"', i + 1);
+    if (j == std::string::npos) break;
+    const unsigned long k = std::strtoul(s.substr(i + 1, j - i - 1).c_str(), nullptr, 10);
+    const size_t colon = s.find(':', j);
+    if (colon == std::string::npos) break;
+    const unsigned long long cnt = std::strtoull(s.c_str() + colon + 1, nullptr, 10);
+    if (k > 65535) die("copy number does not fit u16 in " + path);
+    out[(uint32_t)k] += cnt;
+    i = colon + 1;
+  }
+  if (out.empty()) die("empty distribution in " + path);
+  return out;
+}
+
+// splitmix64 stream for the host-side subsampling (EcDNADistribution::into_subsampled, main.rs:110-123)
+struct SplitMix {
+  uint64_t s;
+  uint64_t next() { uint64_t z = (s += 0x9E3779B97F4A7C15ull); z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull; z = (z ^ (z >> 27)) * 0x94D049BB133111EBull; return z ^ (z >> 31); }
+  uint64_t below(uint64_t n) { const unsigned __int128 m = (unsigned __int128)next() * n; return (uint64_t)(m >> 64); }
+};
+// n cells drawn without replacement from the distribution (multivariate hypergeometric, class by class)
+std::vector<uint32_t> subsample(const uint32_t* hist, uint32_t len, uint64_t n, SplitMix& g) {
+  std::vector<uint32_t> out(len, 0);
+  uint64_t remaining = 0;
+  for (uint32_t k = 0; k < len; ++k) remaining += hist[k];
+  if (n >= remaining) { out.assign(hist, hist + len); return out; }
+  std::vector<uint64_t> left(hist, hist + len);
+  for (uint64_t d = 0; d < n; ++d) {
+    uint64_t r = g.below(remaining);
+    for (uint32_t k = 0; k < len; ++k) {
+      if (r < left[k]) { left[k]--; out[k]++; break; }
+      r -= left[k];
+    }
+    remaining--;
+  }
+  return out;
+}
+
+std::string utc_now() {
+  using namespace std::chrono;
+  const auto now = system_clock::now();
+  const std::time_t t = system_clock::to_time_t(now);
+  const auto ns = duration_cast<nanoseconds>(now.time_since_epoch()).count() % 1000000000ll;
+  char buf[64];
+  std::tm tm{};
+  gmtime_r(&t, &tm);
+  std::strftime(buf, sizeof buf, "%Y-%m-%d %H:%M:%S", &tm);
+  char out[96];
+  std::snprintf(out, sizeof out, "%s.%09lld UTC", buf, (long long)ns);
+  return out;
+}
+
+const char* kStopNames[] = {"NoIndividualsLeft", "MaxItersReached", "MaxTimeReached", "MaxIndividualsReached",
+                            "AbsorbingStateReached", "CopyNumberOverflow", "HistogramOverflow", "ReplayExhausted",
+                            "ReplayInconsistent"};
+
+}  // namespace
+
+int main(int argc, char** argv) {
+  Cli c = parse(argc, argv);
+  if (c.growth == "constant") { std::fprintf(stderr, "not yet implemented\n"); return 101; }  // todo!(), main.rs:49
+  if (c.growth != "exponential") die("invalid value '" + c.growth + "' for '--growth <GROWTH>'");
+  uint32_t seg;
+  if (c.segregation == "deterministic") seg = ECDNA_B200_SEG_DETERMINISTIC;
+  else if (c.segregation == "binomial-no-uneven") seg = ECDNA_B200_SEG_BINOMIAL_NO_UNEVEN;
+  else if (c.segregation == "binomial") seg = ECDNA_B200_SEG_BINOMIAL;
+  else if (c.segregation == "binomial-no-nminus") seg = ECDNA_B200_SEG_BINOMIAL_NO_NMINUS;
+  else die("invalid value '" + c.segregation + "' for '--segregation <SEGREGATION>'");
+
+  // clap_app.rs:140-157
+  uint64_t cells, years, runs;
+  int verbosity;
+  if (c.debug) { cells = 300; years = 2; verbosity = 255; runs = 1; }
+  else if (c.has_years) { cells = kMaxCells; years = c.years; verbosity = c.verbosity; runs = c.runs; }
+  else {
+    cells = c.has_cells ? c.cells : 1000;
+    years = (uint64_t)(log2f((float)cells) + 4.f);
+    verbosity = c.verbosity;
+    runs = c.runs;
+  }
+  // clap_app.rs:102-134
+  std::vector<uint64_t> snapshots;
+  if (c.has_snapshots) snapshots = c.snapshots;
+  else {
+    const uint64_t dx = cells / 10;
+    snapshots.assign(11, 1);
+    for (int i = 1; i < 10; ++i) snapshots[i] = snapshots[i - 1] + dx;
+    snapshots[10] = cells;
+  }
+  std::sort(snapshots.begin(), snapshots.end());
+  // clap_app.rs:165-174
+  const float d0 = c.has_d0 ? c.d0 : 0.f, d1 = c.has_d1 ? c.d1 : 0.f;
+  const bool birth_death = (c.has_d0 && c.d0 > 0.f) || (c.has_d1 && c.d1 > 0.f);
+  // clap_app.rs:177-192
+  std::map<uint32_t, uint64_t> init;
+  if (!c.initial.empty()) init = load_json_hist(c.initial);
+  else init[1] = 1;
+  std::vector<uint16_t> init_k;
+  std::vector<uint64_t> init_c;
+  for (auto& kv : init) { init_k.push_back((uint16_t)kv.first); init_c.push_back(kv.second); }
+
+  std::printf("%s Starting the simulation\n", utc_now().c_str());  // main.rs:53
+
+  ecdna_b200_ctx* ctx = nullptr;
+  int rc = ecdna_b200_create(c.device, &ctx);
+  if (rc != ECDNA_B200_OK) {
+    std::fprintf(stderr, "ecdna_b200_create failed with status %d (no B200 visible? this backend has no CPU path)\n", rc);
+    return 101;
+  }
+  ecdna_b200_params_t p;
+  std::memset(&p, 0, sizeof p);
+  p.abi_version = ECDNA_B200_ABI_VERSION;
+  p.b0 = c.b0; p.b1 = c.b1; p.d0 = d0; p.d1 = d1;
+  p.segregation = seg;
+  p.max_cells = cells; p.max_iter = kMaxIter; p.max_time = (float)years;  // clap_app.rs:204-209
+  p.seed = c.seed;
+  p.n_init = (uint32_t)init_k.size(); p.init_k = init_k.data(); p.init_c = init_c.data();
+  p.n_snapshots = (uint32_t)snapshots.size(); p.snapshot_cells = snapshots.empty() ? nullptr : snapshots.data();
+  p.tile_width = c.tile_width; p.state_mode = c.state_mode;
+  uint32_t stride = 1024;
+
+  const uint64_t idx_begin = c.seed * 10;  // main.rs:214
+  std::vector<uint32_t> stop(runs), kmax(runs), snap_count(runs), hist, snap_hist;
+  std::vector<uint64_t> nminus(runs), nplus(runs), snap_cells(runs * snapshots.size());
+  std::vector<float> time(runs), snap_time(runs * snapshots.size());
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    p.hist_stride = stride;
+    hist.assign((size_t)runs * stride, 0);
+    snap_hist.assign((size_t)runs * snapshots.size() * stride, 0);
+    ecdna_b200_results_t r;
+    std::memset(&r, 0, sizeof r);
+    r.stop_reason = stop.data(); r.nminus = nminus.data(); r.nplus = nplus.data(); r.time = time.data();
+    r.kmax = kmax.data(); r.hist = hist.data();
+    if (!snapshots.empty()) { r.snap_count = snap_count.data(); r.snap_cells = snap_cells.data(); r.snap_time = snap_time.data(); r.snap_hist = snap_hist.data(); }
+    rc = ecdna_b200_run(ctx, &p, idx_begin, runs, &r);
+    if (rc != ECDNA_B200_OK) { std::fprintf(stderr, "ecdna_b200_run: %s\n", ecdna_b200_last_error(ctx)); return 101; }
+    uint32_t top = 0;
+    for (uint64_t i = 0; i < runs; ++i) top = std::max(top, kmax[i]);
+    if (top < stride) break;
+    stride = ((top + 1 + 1023) / 1024) * 1024;  // histograms were truncated: run again with room for them
+  }
+
+  for (uint64_t i = 0; i < runs; ++i) {
+    const uint64_t idx = idx_begin + i;
+    const std::string filename = make_filename(c, birth_death, d0, d1, idx);
+    const uint32_t code = stop[i] & 0xFFu;
+    if (code == ECDNA_B200_STOP_COPY_OVERFLOW) {  // proliferation.rs:63-67 panics: the reference aborts here
+      std::fprintf(stderr, "Overflow while segregating DNA into two daughter cells (idx %llu)\n", (unsigned long long)idx);
+      return 101;
+    }
+    for (uint32_t sidx = 0; sidx < snap_count[i] && !snapshots.empty(); ++sidx) {
+      const size_t o = (size_t)i * snapshots.size() + sidx;
+      if (verbosity > 0) std::printf("saving state for timepoint at time %s with cells %llu \n", rust_f32_to_string(snap_time[o]).c_str(), (unsigned long long)snap_cells[o]);
+      save(c, filename, snap_time[o], snap_hist.data() + o * stride, stride, verbosity);
+    }
+    save(c, filename, time[i], hist.data() + (size_t)i * stride, stride, verbosity);  // main.rs:100-109
+    if (c.has_subsamples) {                                                           // main.rs:110-123
+      SplitMix g{c.seed ^ (idx * 0xD6E8FEB86659FD93ull)};
+      for (uint64_t n : c.subsamples) {
+        const std::vector<uint32_t> sub = subsample(hist.data() + (size_t)i * stride, stride, n, g);
+        save(c, filename, time[i], sub.data(), stride, verbosity);
+      }
+    }
+    if (verbosity > 0)  // main.rs:205-210
+      std::printf("stop reason: %s\nnminus, nplus: [\n    %llu,\n    %llu,\n]\ntime: %s\n", kStopNames[code > 8 ? 8 : code],
+                  (unsigned long long)nminus[i], (unsigned long long)nplus[i], rust_f32_to_string(time[i]).c_str());
+  }
+  ecdna_b200_destroy(ctx);
+  std::printf("%s End simulation\n", utc_now().c_str());  // main.rs:226
+  return 0;
+}

@@ -1,0 +1,86 @@
+"""CPU-side checks of the drop-in boundary: the C ABI library loads, exports every symbol that
+include/ecdna_b200.h declares, agrees with the ctypes mirror on struct layout, and refuses to run
+(rather than falling back) when no B200 is present.  No compute calls are made here."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "ecdna_b200.h")
+
+
+@pytest.fixture(scope="module")
+def built(pkg):
+    pkg.build()
+    return pkg
+
+
+def declared_functions():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(ecdna_b200_[a-z_0-9]+)\s*\(", src)))
+
+
+def test_header_functions_are_exported(built):
+    names = declared_functions()
+    assert len(names) >= 9
+    lib = C.CDLL(built.LIB_PATH)
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/ecdna_b200.h but not exported"
+    assert sorted(built.EXPORTED_SYMBOLS) == names
+    assert lib.ecdna_b200_abi_version() == built.ABI_VERSION
+
+
+def test_no_reference_or_oracle_symbols_in_product(built):
+    """The product library must not link the oracle: no orc_* symbol, no dependency on it."""
+    out = subprocess.run(["nm", "-D", "--defined-only", built.LIB_PATH], capture_output=True, text=True).stdout
+    assert "orc_" not in out
+    ldd = subprocess.run(["ldd", built.LIB_PATH], capture_output=True, text=True).stdout
+    assert "oracle" not in ldd and "torch" not in ldd
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "ecdna-evo_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "oracle_binding" not in txt and "ecdna_oracle" not in txt, f
+
+
+def test_struct_layout_matches_ctypes(built, tmp_path):
+    c = tmp_path / "layout.c"
+    c.write_text('''
+#include <stdio.h>
+#include <stddef.h>
+#include "ecdna_b200.h"
+int main(void) {
+  printf("%zu %zu %zu %zu ", sizeof(ecdna_b200_params_t), sizeof(ecdna_b200_results_t), sizeof(ecdna_b200_timing_t), sizeof(ecdna_b200_replay_event_t));
+  printf("%zu %zu %zu %zu %zu ", offsetof(ecdna_b200_params_t, max_cells), offsetof(ecdna_b200_params_t, seed), offsetof(ecdna_b200_params_t, init_k), offsetof(ecdna_b200_params_t, abc_thresholds), offsetof(ecdna_b200_params_t, spill_records));
+  printf("%zu %zu %zu\\n", offsetof(ecdna_b200_results_t, hist), offsetof(ecdna_b200_timing_t, total_events), offsetof(ecdna_b200_timing_t, n_spilled));
+  return 0;
+}''')
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(c), "-o", str(exe)],
+                   check=True)
+    got = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True).stdout.split()]
+    P, R, T = built.ParamsT, built.ResultsT, built.TimingT
+    want = [C.sizeof(P), C.sizeof(R), C.sizeof(T), built.REPLAY_DTYPE.itemsize,
+            P.max_cells.offset, P.seed.offset, P.init_k.offset, P.abc_thresholds.offset, P.spill_records.offset,
+            R.hist.offset, T.total_events.offset, T.n_spilled.offset]
+    assert got == want
+
+
+def test_header_is_plain_c_with_citations():
+    src = open(HEADER).read()
+    assert 'extern "C"' in src and "torch" not in src and "std::" not in src
+    for cite in ("main.rs:55-211", "main.rs:28-44", "process.rs:31-55", "clap_app.rs:232-238", "proliferation.rs:63-67"):
+        assert cite in src
+
+
+def test_no_gpu_means_error_not_fallback(built):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present; covered by the gpu tests")
+    with pytest.raises(built.EcdnaB200Error) as e:
+        built.Context(0)
+    assert "status 3" in str(e.value)
