@@ -73,10 +73,10 @@ int fail(ecdna_b200_ctx* ctx, int code, const std::string& msg) {
   } while (0)
 
 // one launch of ssa_kernel<L, GLOBAL, REPLAY>; returns the grid used through *grid_out
-template <int L, bool GLOBAL, bool REPLAY>
+template <int L, bool GLOBAL, bool REPLAY, int KG>
 int launch_kernel(ecdna_b200_ctx* ctx, SsaArgs& a, cudaStream_t st, uint64_t max_items, uint32_t* grid_out,
                   uint32_t* bps_out) {
-  auto kern = ssa_kernel<L, GLOBAL, REPLAY>;
+  auto kern = ssa_kernel<L, GLOBAL, REPLAY, KG>;
   const int warps = kBlockThreads / 32;
   const int tiles_per_block = kBlockThreads / L;
   const size_t smem = GLOBAL ? 0 : (size_t)warps * Tile<L, GLOBAL>::window_words(a.kcap_s) * sizeof(uint32_t);
@@ -118,19 +118,23 @@ int launch_all(ecdna_b200_ctx* ctx, SsaArgs& a, cudaStream_t st, const ecdna_b20
   if (p->state_mode == ECDNA_B200_STATE_HBM) {
     a.park_list = nullptr;
     a.allow_park = 0;
-    int rc = launch_kernel<32, true, REPLAY>(ctx, a, st, a.n_runs, &grid, &bps);
+    int rc = launch_kernel<32, true, REPLAY, 0>(ctx, a, st, a.n_runs, &grid, &bps);
     if (rc) return rc;
     tm.kernel_launches = 1;
     tm.tile_width = 32;
   } else {
     a.allow_park = p->state_mode == ECDNA_B200_STATE_AUTO ? 1u : 0u;
-    int rc = launch_kernel<L, false, REPLAY>(ctx, a, st, a.n_runs, &grid, &bps);
+    // the walk over the shared window is unrolled for the two common window sizes
+    int rc;
+    if (!REPLAY && a.kcap_s == 256) rc = launch_kernel<L, false, REPLAY, 2>(ctx, a, st, a.n_runs, &grid, &bps);
+    else if (!REPLAY && a.kcap_s == 512) rc = launch_kernel<L, false, REPLAY, 4>(ctx, a, st, a.n_runs, &grid, &bps);
+    else rc = launch_kernel<L, false, REPLAY, 0>(ctx, a, st, a.n_runs, &grid, &bps);
     if (rc) return rc;
     tm.kernel_launches = 1;
     tm.tile_width = L;
     if (a.allow_park) {
       uint32_t g2 = 0, b2 = 0;
-      rc = launch_kernel<32, true, REPLAY>(ctx, a, st, a.n_runs, &g2, &b2);
+      rc = launch_kernel<32, true, REPLAY, 0>(ctx, a, st, a.n_runs, &g2, &b2);
       if (rc) return rc;
       tm.kernel_launches = 2;
     }
