@@ -258,7 +258,12 @@ int run_common(ecdna_b200_ctx* ctx, const ecdna_b200_params_t* p, uint64_t idx_b
   a.n_runs = (uint32_t)n_runs;
   a.dyn_points = p->dyn_points; a.dyn_dt = p->dyn_dt;
   a.flags = p->flags;
-  a.kcap_s = p->smem_bins ? ((p->smem_bins + 127u) & ~127u) : 512u;  // bins come in rows of 4 x 32
+  // tile width: sub-warp tiles divide the instructions per event by 32/L but need enough replicates
+  // to keep every SM busy; measured on B200 (profiles/): 4-lane tiles win from ~1.5k replicates up,
+  // below that a replicate per warp has the shortest event latency
+  const uint32_t L = p->tile_width ? p->tile_width : (n_runs >= 1536 ? 4u : 32u);
+  const uint32_t default_bins = L == 4 ? 256u : 512u;  // 4-lane tiles: 8 replicates per warp window
+  a.kcap_s = p->smem_bins ? ((p->smem_bins + 127u) & ~127u) : default_bins;  // bins come in rows of 4 x 32
   a.kcap_g = ((p->max_copies ? p->max_copies : 65535u) + 128u) & ~127u;
   if (a.kcap_g < a.kcap_s) a.kcap_g = a.kcap_s;
   a.hist_stride = p->hist_stride ? p->hist_stride : 512u;
@@ -372,7 +377,6 @@ int run_common(ecdna_b200_ctx* ctx, const ecdna_b200_params_t* p, uint64_t idx_b
     a.park_cap = (uint32_t)cap;
   }
 
-  const uint32_t L = p->tile_width ? p->tile_width : 32u;
   if (L == 32) rc = replay ? launch_all<32, true>(ctx, a, st, p) : launch_all<32, false>(ctx, a, st, p);
   else if (L == 16) rc = replay ? launch_all<16, true>(ctx, a, st, p) : launch_all<16, false>(ctx, a, st, p);
   else if (L == 8) rc = replay ? launch_all<8, true>(ctx, a, st, p) : launch_all<8, false>(ctx, a, st, p);

@@ -139,6 +139,65 @@ def test_replay_bit_exact(pkg, ctx, name, rng):
         assert (h.hash, h.chain, h.n_events) == (ref.hash, ref.chain, ref.n_events)
 
 
+def test_kernel_matches_golden_fixtures(pkg, ctx):
+    """The committed fixtures (tests/golden/golden_v1.json, frozen from the oracle) through the C ABI."""
+    import json
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import make_golden
+    gold = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_v1.json")))
+    seg_names = {v: k for k, v in pkg.SEGREGATION_NAMES.items()}
+    for name, kw in make_golden.CASES.items():
+        o = pkg.SimulationOptions(b0=kw.get("b0", 1.0), b1=kw.get("b1", 1.0), d0=kw.get("d0"), d1=kw.get("d1"),
+                                  cells=kw["max_cells"], initial=kw.get("initial"), runs=4, save_snapshots=False,
+                                  segregation=seg_names[kw.get("segregation", ob.SEG_BINOMIAL)])
+        for tile in (0, 32, 4):
+            res = ctx.run(o, want=WANT, digest=True, tile_width=tile)
+            for i, want in enumerate(gold["native"][name]):
+                got = {"stop": int(res.stop[i]), "nminus": int(res.nminus[i]), "nplus": int(res.nplus[i]),
+                       "n_events": int(res.n_events[i]), "time_bits": int(res.time[i:i + 1].view(np.uint32)[0]),
+                       "kmax": int(res.kmax[i]), "hash": int(res.hash[i]), "chain": int(res.chain[i]),
+                       "hist": {str(k): int(c) for k, c in enumerate(res.hist[i]) if c}}
+                assert got == want, (name, tile, i)
+
+
+def test_cli_writes_reference_layout(pkg, ctx, tmp_path):
+    """The drop-in `ecdna` binary: same flags, same files (process.rs:39-45, lib.rs:27-45) and the
+    histograms in them equal the library's (and therefore the oracle's)."""
+    import json
+    import os
+    import subprocess
+    pkg.build()
+    exe = os.path.join(os.path.dirname(pkg.LIB_PATH), "host", "ecdna")
+    out = str(tmp_path / "out")
+    cmd = [exe, "--b1", "1.5", "--d0", "0.1", "--d1", "0.2", "--cells", "500", "--runs", "3", "--seed", "7",
+           "--snapshots=1,100,500", "--subsamples=50", out]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert "Starting the simulation" in r.stdout and "End simulation" in r.stdout
+    o = pkg.SimulationOptions(b1=1.5, d0=0.1, d1=0.2, cells=500, runs=3, seed=7, snapshots=[1, 100, 500])
+    res = ctx.run(o, want=WANT + ("snap_count", "snap_cells", "snap_time", "snap_hist"))
+    for i in range(3):
+        name = f"1b0_1dot5b1_0dot1d0_0dot2d1_{70 + i}idx.json"
+        cells = int(res.nminus[i] + res.nplus[i])
+        t = f"{float(res.time[i]):.1f}".replace(".", "dot") + "years"
+        final = json.load(open(os.path.join(out, f"{cells}cells", "ecdna", t, name)))
+        assert final == {str(k): int(c) for k, c in enumerate(res.hist[i]) if c}
+        for s in range(int(res.snap_count[i])):
+            sc = int(res.snap_cells[i][s])
+            st = f"{float(res.snap_time[i][s]):.1f}".replace(".", "dot") + "years"
+            snap = json.load(open(os.path.join(out, f"{sc}cells", "ecdna", st, name)))
+            assert sum(snap.values()) == sc
+        if cells > 50:
+            sub = [p for p in os.listdir(os.path.join(out, "50cells", "ecdna")) if p == t]
+            assert sub, "subsample directory missing"
+            assert sum(json.load(open(os.path.join(out, "50cells", "ecdna", t, name))).values()) == 50
+    # clap-compatible errors
+    assert subprocess.run([exe, "--years", "3", "--cells", "4", out], capture_output=True).returncode == 2
+    assert subprocess.run([exe], capture_output=True).returncode == 2
+
+
 def test_replay_detects_inconsistency(pkg, ctx):
     o = pkg.SimulationOptions(runs=1, cells=200, save_snapshots=False)
     r = _vector_trace(o, o.idx_begin, ob.RNG_RAND)
