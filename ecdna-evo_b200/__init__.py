@@ -17,6 +17,7 @@ import numpy as np
 
 from .build import LIB_PATH, build  # noqa: F401
 from .shard import gather_accepted, rank_range  # noqa: F401
+from .abc import ABC_FIELDS, abc_rows, write_abc_csv  # noqa: F401
 
 ABI_VERSION = 1
 EV_BIRTH_NMINUS, EV_BIRTH_NPLUS, EV_DEATH_NMINUS, EV_DEATH_NPLUS = 0, 1, 2, 3

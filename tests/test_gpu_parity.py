@@ -273,6 +273,37 @@ def test_abc_epilogue_matches_oracle(pkg, ctx):
     assert 0 < n_acc < n
 
 
+def test_native_distribution_matches_reference_layout(pkg, ctx):
+    """North-star criterion for native mode: against the reference-layout oracle (per-cell vector,
+    ChaCha8 + rand conversions, ziggurat, BINV/BTPE) over 10^4 replicates each, two-sample KS p > 0.01
+    on the per-replicate mean / frequency / entropy / clock, their means inside 99% CIs, the same
+    extinction probability, and matching pooled final ecDNA distributions."""
+    from scipy import stats as sps
+    n = 10000
+    o = pkg.SimulationOptions(b0=1.0, b1=1.3, d0=0.1, d1=0.15, cells=3000, runs=n, save_snapshots=False)
+    g = ctx.run(o, want=WANT, hist_stride=256)
+    ref = ob.run_batch(oracle_opts(o, 0, state=ob.STATE_VECTOR, rng=ob.RNG_RAND), 10 ** 6, n, hist_cap=256)
+    ga, ra = g.stop == pkg.STOP_MAX_CELLS, ref.stop == ob.STOP_MAX_CELLS
+    pg, pr = 1 - ga.mean(), 1 - ra.mean()
+    assert abs(pg - pr) < 2.58 * np.sqrt((pg * (1 - pg) + pr * (1 - pr)) / n)
+    rstats = np.array([ob.stats(h) for h in ref.hist[ra]])
+    samples = {"mean": (g.mean[ga], rstats[:, 0]), "frequency": (g.frequency[ga], rstats[:, 1]),
+               "entropy": (g.entropy[ga], rstats[:, 2]), "clock": (g.time[ga], ref.time[ra])}
+    for name, (a, b) in samples.items():
+        a, b = a.astype(np.float64), b.astype(np.float64)
+        assert sps.ks_2samp(a, b).pvalue > 0.01, name
+        se = np.sqrt(a.var() / len(a) + b.var() / len(b))
+        assert abs(a.mean() - b.mean()) < 2.58 * se, name
+    # pooled final ecDNA distribution: per-class frequencies agree within the between-replicate spread
+    hg, hr = g.hist[ga].astype(np.float64), ref.hist[ra].astype(np.float64)
+    fg, fr = hg / hg.sum(axis=1, keepdims=True), hr / hr.sum(axis=1, keepdims=True)
+    se = np.sqrt(fg.var(axis=0) / len(fg) + fr.var(axis=0) / len(fr)) + 1e-9
+    z = np.abs(fg.mean(axis=0) - fr.mean(axis=0)) / se
+    busy = (fg.mean(axis=0) + fr.mean(axis=0)) > 1e-3
+    assert (z[busy] > 3.5).sum() <= 1 and z[busy].max() < 5.0
+    assert sps.ks_2samp(fg.mean(axis=0).cumsum(), fr.mean(axis=0).cumsum()).pvalue > 0.01
+
+
 def test_full_size_properties(pkg, ctx):
     """BASELINE config 1 at full size (1e5 cells, 100 replicates): size-independent invariants."""
     o = pkg.SimulationOptions(cells=100000, runs=100, save_snapshots=False)

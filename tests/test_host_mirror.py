@@ -48,3 +48,21 @@ def test_save_layout(pkg, tmp_path):
     p = pkg.save(str(tmp_path), "1b0_1b1_0d0_0d1_260idx", 3.14159, hist)
     assert p == os.path.join(str(tmp_path), "6cells", "ecdna", "3dot1years", "1b0_1b1_0d0_0d1_260idx.json")
     assert json.load(open(p)) == {"0": 2, "1": 2, "10": 1, "20": 1}
+
+
+def test_abc_csv_schema(pkg, tmp_path):
+    # abc.md:38-55: one row per draw, all draws kept; f1/d1 = cells with ecDNA, f2/d2 = without
+    import csv
+    o = pkg.SimulationOptions(b0=1.0, b1=1.4, d0=0.2, d1=0.2, cells=1000, initial={2: 3, 0: 1})
+    rates = np.array([[1.0, 1.3, 0.1, 0.2], [1.0, 1.7, 0.3, 0.4]], dtype=np.float32)
+    dist = np.array([[0.05, 0.1, 0.2, 0.3], [0.5, 0.6, 0.7, 0.8]], dtype=np.float32)
+    p = str(tmp_path / "abc.csv")
+    assert pkg.write_abc_csv(p, o, 260, rates, dist, [10, 0], [990, 0]) == 2
+    rows = list(csv.DictReader(open(p)))
+    assert list(rows[0].keys()) == pkg.ABC_FIELDS
+    assert rows[0]["idx"] == "260" and rows[1]["idx"] == "261" and rows[0]["seed"] == "26"
+    assert abs(float(rows[0]["f1"]) - 1.3) < 1e-6 and abs(float(rows[0]["f2"]) - 1.0) < 1e-6
+    assert abs(float(rows[0]["d1"]) - 0.2) < 1e-6 and abs(float(rows[0]["d2"]) - 0.1) < 1e-6
+    assert rows[0]["tumour_cells"] == "1000" and rows[1]["tumour_cells"] == "0"
+    assert float(rows[0]["init_mean"]) == 1.5 and rows[0]["init_cells"] == "4" and rows[0]["init_copies"] == "6"
+    assert abs(float(rows[1]["ecdna"]) - 0.5) < 1e-6
