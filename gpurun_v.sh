@@ -1,5 +1,3 @@
-python -m pytest tests/test_gpu_parity.py -x -q -m gpu 2>&1 | tail -1
-TILE=4 REPS=2 RUNS=40000 BINS=256 python scripts/prof_case.py
-TILE=4 REPS=2 RUNS=160000 BINS=256 python scripts/prof_case.py
-TILE=4 REPS=2 RUNS=10000 BINS=256 python scripts/prof_case.py
-TILE=32 REPS=2 RUNS=1000 python scripts/prof_case.py
+timeout 600 python -m pytest tests -x -q -m gpu --timeout 60 --timeout-method=thread 2>&1 | tail -4
+timeout 100 python __graft_entry__.py smoke
+timeout 300 python bench.py --steps 2 --warmup 3 --no-abc --cpu-seconds 5 | cut -c1-400

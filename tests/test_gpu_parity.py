@@ -29,11 +29,11 @@ def assert_run_equal(res, i, ref, stride, digest=True):
     assert np.float32(res.time[i]).view(np.uint32) == np.float32(ref.time).view(np.uint32)
     assert int(res.kmax[i]) == ref.kmax
     np.testing.assert_array_equal(res.hist[i].astype(np.uint64), ref.hist[:stride])
+    assert int(res.sum_k[i]) == ref.sum_k
+    assert int(res.n_div[i]) == ref.n_div and int(res.n_death[i]) == ref.n_death
     if digest:
         assert int(res.hash[i]) == ref.hash
         assert int(res.chain[i]) == ref.chain
-        assert int(res.sum_k[i]) == ref.sum_k
-        assert int(res.n_div[i]) == ref.n_div and int(res.n_death[i]) == ref.n_death
 
 
 WANT = ("stop_reason", "nminus", "nplus", "time", "n_events", "kmax", "hist", "hash", "chain", "sum_k", "n_div",
@@ -58,14 +58,17 @@ CASES = {
 }
 
 
+@pytest.mark.parametrize("digest", [False, True], ids=["straight", "digest"])
 @pytest.mark.parametrize("name", sorted(CASES))
-def test_native_bit_exact(pkg, ctx, name):
-    """Native (Philox) mode reproduces the histogram oracle bit for bit, every replicate."""
+def test_native_bit_exact(pkg, ctx, name, digest):
+    """Native (Philox) mode reproduces the histogram oracle bit for bit, every replicate.  Without the
+    digest the kernel runs its straight-line event step (rare events redone by the complete step);
+    with it every event takes the complete step and the per-event chain digest is compared too."""
     o = pkg.SimulationOptions(runs=12, save_snapshots=False, **CASES[name])
-    res = ctx.run(o, want=WANT, digest=True)
+    res = ctx.run(o, want=WANT, digest=digest)
     for i in range(o.runs):
         ref = ob.run(oracle_opts(o, o.idx_begin + i), hist_cap=512)
-        assert_run_equal(res, i, ref, 512)
+        assert_run_equal(res, i, ref, 512, digest=digest)
         m, f, e, v = ob.stats(ref.hist)
         np.testing.assert_allclose([res.mean[i], res.frequency[i], res.entropy[i]], [m, f, e], rtol=STAT_RTOL, atol=1e-6)
         np.testing.assert_allclose(res.variance[i], v, rtol=1e-4, atol=1e-4)
@@ -77,11 +80,12 @@ def test_native_bit_exact(pkg, ctx, name):
 def test_tile_widths_agree(pkg, ctx, name, tile_width):
     """Sub-warp tiles (several replicates per warp) give the same bits as one warp per replicate."""
     o = pkg.SimulationOptions(runs=37, save_snapshots=False, **CASES[name])
-    a = ctx.run(o, want=WANT, digest=True)
-    b = ctx.run(o, want=WANT, digest=True, tile_width=tile_width)
-    for f in ("stop_reason", "nminus", "nplus", "n_events", "kmax", "hist", "hash", "chain", "sum_k"):
-        np.testing.assert_array_equal(getattr(a, f), getattr(b, f), err_msg=f)
-    np.testing.assert_array_equal(a.time.view(np.uint32), b.time.view(np.uint32))
+    a = ctx.run(o, want=WANT, digest=True, tile_width=32)
+    for digest in (True, False):
+        b = ctx.run(o, want=WANT, digest=digest, tile_width=tile_width)
+        for f in ("stop_reason", "nminus", "nplus", "n_events", "kmax", "hist", "sum_k") + (("hash", "chain") if digest else ()):
+            np.testing.assert_array_equal(getattr(a, f), getattr(b, f), err_msg=f)
+        np.testing.assert_array_equal(a.time.view(np.uint32), b.time.view(np.uint32))
 
 
 @pytest.mark.parametrize("mode", ["hbm", "spill_resume", "spill_restart", "spill_mixed_l8"])
@@ -93,10 +97,11 @@ def test_hbm_state_bit_exact(pkg, ctx, name, mode):
     kw = {"hbm": dict(state_mode=pkg.STATE_HBM), "spill_resume": dict(smem_bins=128),
           "spill_restart": dict(smem_bins=128, spill_records=0xFFFFFFFF),
           "spill_mixed_l8": dict(smem_bins=128, spill_records=3, tile_width=8)}[mode]
-    res = ctx.run(o, want=WANT, digest=True, **kw)
-    for i in range(o.runs):
-        ref = ob.run(oracle_opts(o, o.idx_begin + i), hist_cap=512)
-        assert_run_equal(res, i, ref, 512)
+    for digest in (True, False):
+        res = ctx.run(o, want=WANT, digest=digest, **kw)
+        for i in range(o.runs):
+            ref = ob.run(oracle_opts(o, o.idx_begin + i), hist_cap=512)
+            assert_run_equal(res, i, ref, 512, digest=digest)
     if mode != "hbm":
         assert res.timing.n_spilled > 0 and np.any(res.stop_reason & pkg.FLAG_SPILLED)
         assert res.timing.kernel_launches == 2
@@ -217,10 +222,10 @@ def test_snapshots_match_oracle(pkg, ctx):
     o = pkg.SimulationOptions(b0=1.0, b1=1.2, d0=0.2, d1=0.2, cells=3000, runs=8, initial={2: 40, 0: 11},
                               snapshots=[1, 51, 60, 500, 1000, 3000])
     want = WANT + ("snap_count", "snap_cells", "snap_time", "snap_hist")
-    res = ctx.run(o, want=want, digest=True)
+    res = ctx.run(o, want=want, digest=False, tile_width=4)
     for i in range(o.runs):
         ref = ob.run(oracle_opts(o, o.idx_begin + i, snapshots=o.snapshots), hist_cap=512)
-        assert_run_equal(res, i, ref, 512)
+        assert_run_equal(res, i, ref, 512, digest=False)
         assert int(res.snap_count[i]) == ref.n_snap_taken
         n = ref.n_snap_taken
         np.testing.assert_array_equal(res.snap_cells[i][:n], ref.snap_cells[:n])
@@ -257,12 +262,12 @@ def test_abc_epilogue_matches_oracle(pkg, ctx):
     assert np.all(rates[:, 0] == 1.0) and np.all((rates[:, 1] >= 1.0) & (rates[:, 1] <= 2.0))
     thr = (0.2, 0.5, 0.5, 0.5)
     res = ctx.run(o, want=WANT + ("abc_distance", "abc_accept"), rates_per_run=rates, abc_target=target,
-                  abc_thresholds=thr, digest=True)
+                  abc_thresholds=thr, digest=False, tile_width=4)
     tm, tf, te, _ = ob.stats(target)
     n_acc = 0
     for i in range(n):
         ref = ob.run(oracle_opts(o, o.idx_begin + i, rates=rates[i]), hist_cap=512)
-        assert_run_equal(res, i, ref, 512)
+        assert_run_equal(res, i, ref, 512, digest=False)
         m, f, e, _ = ob.stats(ref.hist)
         want = [ob.ks_distance(ref.hist, target), abs(m - tm) / tm, abs(e - te) / te, abs(f - tf) / tf]
         np.testing.assert_allclose(res.abc_distance[i], want, rtol=1e-4, atol=1e-5)
@@ -301,7 +306,15 @@ def test_native_distribution_matches_reference_layout(pkg, ctx):
     z = np.abs(fg.mean(axis=0) - fr.mean(axis=0)) / se
     busy = (fg.mean(axis=0) + fr.mean(axis=0)) > 1e-3
     assert (z[busy] > 3.5).sum() <= 1 and z[busy].max() < 5.0
-    assert sps.ks_2samp(fg.mean(axis=0).cumsum(), fr.mean(axis=0).cumsum()).pvalue > 0.01
+    assert np.abs(fg.mean(axis=0).cumsum() - fr.mean(axis=0).cumsum()).max() < 0.008
+    # two-sample KS on the final ecDNA distribution with independent samples: one random cell per replicate
+    rng = np.random.default_rng(5)
+
+    def one_cell(f):
+        u = rng.random(len(f))
+        return (f.cumsum(axis=1) < u[:, None]).sum(axis=1)
+
+    assert sps.ks_2samp(one_cell(fg), one_cell(fr)).pvalue > 0.01
 
 
 def test_full_size_properties(pkg, ctx):
