@@ -55,6 +55,9 @@ CASES = {
     "wide": dict(b0=1.0, b1=1.3, cells=8000, initial={100: 1}),
     "wide_bd": dict(b0=1.0, b1=1.2, d0=0.1, d1=0.2, cells=6000, initial={120: 3, 0: 5, 7: 2}),
     "wide_initial": dict(b0=1.0, b1=1.1, cells=3000, initial={200: 2, 3: 1, 130: 1}),
+    # copy numbers near the top of u16: segregation draws of up to 62000 bits (hundreds of Philox slots),
+    # HBM arena walked over hundreds of rows, and the u16 doubling overflow somewhere along the way
+    "huge_k": dict(b0=1.0, b1=1.0, d1=0.2, cells=40, initial={20000: 2, 31000: 1, 9: 1}),
 }
 
 
@@ -65,10 +68,11 @@ def test_native_bit_exact(pkg, ctx, name, digest):
     digest the kernel runs its straight-line event step (rare events redone by the complete step);
     with it every event takes the complete step and the per-event chain digest is compared too."""
     o = pkg.SimulationOptions(runs=12, save_snapshots=False, **CASES[name])
-    res = ctx.run(o, want=WANT, digest=digest)
+    stride = 65536 if name == "huge_k" else 512
+    res = ctx.run(o, want=WANT, digest=digest, hist_stride=stride)
     for i in range(o.runs):
-        ref = ob.run(oracle_opts(o, o.idx_begin + i), hist_cap=512)
-        assert_run_equal(res, i, ref, 512, digest=digest)
+        ref = ob.run(oracle_opts(o, o.idx_begin + i), hist_cap=stride)
+        assert_run_equal(res, i, ref, stride, digest=digest)
         m, f, e, v = ob.stats(ref.hist)
         np.testing.assert_allclose([res.mean[i], res.frequency[i], res.entropy[i]], [m, f, e], rtol=STAT_RTOL, atol=1e-6)
         np.testing.assert_allclose(res.variance[i], v, rtol=1e-4, atol=1e-4)
@@ -89,7 +93,7 @@ def test_tile_widths_agree(pkg, ctx, name, tile_width):
 
 
 @pytest.mark.parametrize("mode", ["hbm", "spill_resume", "spill_restart", "spill_mixed_l8"])
-@pytest.mark.parametrize("name", ["wide", "wide_bd", "wide_initial"])
+@pytest.mark.parametrize("name", ["wide", "wide_bd", "wide_initial", "huge_k"])
 def test_hbm_state_bit_exact(pkg, ctx, name, mode):
     """The HBM-resident histogram, and parking a replicate that outgrows shared memory (with its
     state saved, or restarted from event 0 when no record slot is left), do not change a single bit."""
@@ -97,11 +101,12 @@ def test_hbm_state_bit_exact(pkg, ctx, name, mode):
     kw = {"hbm": dict(state_mode=pkg.STATE_HBM), "spill_resume": dict(smem_bins=128),
           "spill_restart": dict(smem_bins=128, spill_records=0xFFFFFFFF),
           "spill_mixed_l8": dict(smem_bins=128, spill_records=3, tile_width=8)}[mode]
+    stride = 65536 if name == "huge_k" else 512
     for digest in (True, False):
-        res = ctx.run(o, want=WANT, digest=digest, **kw)
+        res = ctx.run(o, want=WANT, digest=digest, hist_stride=stride, **kw)
         for i in range(o.runs):
-            ref = ob.run(oracle_opts(o, o.idx_begin + i), hist_cap=512)
-            assert_run_equal(res, i, ref, 512, digest=digest)
+            ref = ob.run(oracle_opts(o, o.idx_begin + i), hist_cap=stride)
+            assert_run_equal(res, i, ref, stride, digest=digest)
     if mode != "hbm":
         assert res.timing.n_spilled > 0 and np.any(res.stop_reason & pkg.FLAG_SPILLED)
         assert res.timing.kernel_launches == 2
@@ -346,6 +351,19 @@ def test_copy_overflow_is_reported_not_fatal(pkg, ctx):
     assert np.all(res.stop == pkg.STOP_COPY_OVERFLOW)
     ref = ob.run(oracle_opts(o, o.idx_begin), hist_cap=64)
     assert ref.stop_reason == ob.STOP_COPY_OVERFLOW
+
+
+def test_single_replicate_and_ragged_batches(pkg, ctx):
+    """Batch sizes that do not fill a tile group, a warp or a block give the same replicates."""
+    o = pkg.SimulationOptions(b0=1.0, b1=1.3, d0=0.1, d1=0.1, cells=2000, runs=67, save_snapshots=False)
+    full = ctx.run(o, want=WANT, tile_width=4)
+    for n in (1, 3, 9, 33):
+        part = ctx.run(o, n_runs=n, want=WANT, tile_width=4)
+        for f in ("stop_reason", "nminus", "nplus", "n_events", "kmax", "hist"):
+            np.testing.assert_array_equal(getattr(part, f), getattr(full, f)[:n], err_msg=f)
+    # a later index range is the same as the tail of a longer one (replicates are keyed by index)
+    tail = ctx.run(o, n_runs=7, idx_begin=o.idx_begin + 60, want=WANT)
+    np.testing.assert_array_equal(tail.hist, full.hist[60:])
 
 
 def test_bad_params_are_errors(pkg, ctx):
