@@ -19,31 +19,51 @@ def _nvcc():
     raise RuntimeError("nvcc not found: libecdna_b200.so cannot be built (there is no CPU fallback)")
 
 
-def _stale(target, sources):
-    if not os.path.exists(target):
+def _digest(sources, extra=""):
+    import hashlib
+    h = hashlib.sha256(extra.encode())
+    for s in sorted(sources):
+        h.update(os.path.basename(s).encode())
+        with open(s, "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()
+
+
+def _stale(target, sources, extra=""):
+    """Stale = built from different source CONTENT (mtimes do not survive copying the tree)."""
+    stamp = target + ".srchash"
+    if not os.path.exists(target) or not os.path.exists(stamp):
         return True
-    t = os.path.getmtime(target)
-    return any(os.path.getmtime(s) > t for s in sources)
+    return open(stamp).read().strip() != _digest(sources, extra)
+
+
+def _stamp(target, sources, extra=""):
+    with open(target + ".srchash", "w") as f:
+        f.write(_digest(sources, extra))
 
 
 def build(force=False, verbose=False):
     """Compile csrc/*.cu into libecdna_b200.so and host/*.cpp into the `ecdna` CLI."""
     srcs = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC))] + [os.path.join(ROOT, "include", "ecdna_b200.h")]
-    if force or _stale(LIB_PATH, srcs):
+    flags = " ".join(NVCC_FLAGS)
+    if force or _stale(LIB_PATH, srcs, flags):
         cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + [
             "-o", LIB_PATH, os.path.join(CSRC, "capi.cu")]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
+        _stamp(LIB_PATH, srcs, flags)
         if verbose:
             print(r.stderr)
     host_dir = os.path.join(PKG_DIR, "host")
     host_srcs = [os.path.join(host_dir, f) for f in sorted(os.listdir(host_dir)) if f.endswith((".cpp", ".h"))]
-    if host_srcs and (force or _stale(CLI_PATH, host_srcs + [LIB_PATH])):
+    hdr = [os.path.join(ROOT, "include", "ecdna_b200.h")]
+    if host_srcs and (force or _stale(CLI_PATH, host_srcs + hdr)):
         cmd = ["g++", "-O2", "-std=c++17", "-I", os.path.join(ROOT, "include"), "-o", CLI_PATH] + [
             s for s in host_srcs if s.endswith(".cpp")] + ["-L", PKG_DIR, "-lecdna_b200", "-Wl,-rpath,$ORIGIN/..",
                                                             "-ldl", "-lpthread"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("g++ (host CLI) failed:\n" + r.stdout + r.stderr)
+        _stamp(CLI_PATH, host_srcs + hdr)
     return LIB_PATH
