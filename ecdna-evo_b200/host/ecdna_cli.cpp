@@ -46,6 +46,9 @@ struct Cli {
   bool has_subsamples = false, has_snapshots = false;
   std::vector<uint64_t> subsamples, snapshots;
   int verbosity = 0;
+  // outputs the reference dropped after 0.19/0.23 (CHANGELOG.md:14-16, 34-40), off by default
+  bool summaries = false;  // mean / frequency / entropy of the final distribution
+  bool dynamics = false;   // 300 samples of (nminus, nplus, mean, variance, entropy) every 0.1 time units
   // engine knobs (not in the reference)
   int device = 0;
   uint32_t tile_width = 0, state_mode = 0;
@@ -80,6 +83,8 @@ void usage() {
       "      --subsamples[=<N>...]        Subsample the ecDNA distribution at the end of the simulation\n"
       "      --snapshots[=<N>...]         Number of cells that will trigger the saving of the distribution\n"
       "  -v, --verbosity...\n"
+      "      --summaries                  also write <cells>cells/{mean,frequency,entropy}/<t>years/<name>.json\n"
+      "      --dynamics                   also write <cells>cells/dynamics/<t>years/<name>.json (300 x 0.1)\n"
       "      --device <N>  --tile-width <4|8|16|32>  --state <auto|smem|hbm>   (B200 engine knobs)\n"
       "  -h, --help\n  -V, --version");
 }
@@ -128,6 +133,8 @@ Cli parse(int argc, char** argv) {
     else if (a == "-r" || a == "--runs") { c.runs = std::strtoull(value().c_str(), nullptr, 10); runs_given = true; }
     else if (a == "--subsamples") { c.has_subsamples = true; if (has_eq) c.subsamples = parse_list(val); }  // require_equals
     else if (a == "--snapshots") { c.has_snapshots = true; if (has_eq) c.snapshots = parse_list(val); }
+    else if (a == "--summaries") c.summaries = true;
+    else if (a == "--dynamics") c.dynamics = true;
     else if (a == "--device") c.device = std::atoi(value().c_str());
     else if (a == "--tile-width") c.tile_width = (uint32_t)std::atoi(value().c_str());
     else if (a == "--state") {
@@ -220,6 +227,17 @@ void save(const Cli& c, const std::string& filename, float time, const uint32_t*
     first = false;
   }
   f << "}";
+}
+
+// same directory scheme as `save`, with the measurement name in place of "ecdna"
+std::string measurement_path(const Cli& c, uint64_t cells, float time, const char* what, const std::string& filename) {
+  char tbuf[64];
+  std::snprintf(tbuf, sizeof tbuf, "%.1f", (double)time);
+  std::string tp;
+  for (const char* p = tbuf; *p; ++p) { if (*p == '.') tp += "dot"; else tp.push_back(*p); }
+  const std::string dir = c.path + "/" + std::to_string(cells) + "cells/" + what + "/" + tp + "years";
+  mkdirs(dir);
+  return dir + "/" + filename + ".json";
 }
 
 // {"0": 2, "1": 2, "10": 1} (dynamics.md:7-8)
@@ -355,6 +373,11 @@ int main(int argc, char** argv) {
   std::vector<uint32_t> stop(runs), kmax(runs), snap_count(runs), hist, snap_hist;
   std::vector<uint64_t> nminus(runs), nplus(runs), snap_cells(runs * snapshots.size());
   std::vector<float> time(runs), snap_time(runs * snapshots.size());
+  const uint32_t dyn_points = c.dynamics ? 300u : 0u;  // CHANGELOG.md:34-36
+  std::vector<float> mean(runs), freq(runs), entropy(runs), dyn((size_t)runs * dyn_points * 5);
+  std::vector<uint32_t> dyn_count(runs);
+  p.dyn_points = dyn_points;
+  p.dyn_dt = 0.1f;
   for (int attempt = 0; attempt < 2; ++attempt) {
     p.hist_stride = stride;
     hist.assign((size_t)runs * stride, 0);
@@ -364,6 +387,8 @@ int main(int argc, char** argv) {
     r.stop_reason = stop.data(); r.nminus = nminus.data(); r.nplus = nplus.data(); r.time = time.data();
     r.kmax = kmax.data(); r.hist = hist.data();
     if (!snapshots.empty()) { r.snap_count = snap_count.data(); r.snap_cells = snap_cells.data(); r.snap_time = snap_time.data(); r.snap_hist = snap_hist.data(); }
+    if (c.summaries) { r.mean = mean.data(); r.frequency = freq.data(); r.entropy = entropy.data(); }
+    if (c.dynamics) { r.dyn = dyn.data(); r.dyn_count = dyn_count.data(); }
     rc = ecdna_b200_run(ctx, &p, idx_begin, runs, &r);
     if (rc != ECDNA_B200_OK) { std::fprintf(stderr, "ecdna_b200_run: %s\n", ecdna_b200_last_error(ctx)); return 101; }
     uint32_t top = 0;
@@ -386,6 +411,28 @@ int main(int argc, char** argv) {
       save(c, filename, snap_time[o], snap_hist.data() + o * stride, stride, verbosity);
     }
     save(c, filename, time[i], hist.data() + (size_t)i * stride, stride, verbosity);  // main.rs:100-109
+    if (c.summaries) {
+      const uint64_t cells_now = nminus[i] + nplus[i];
+      const std::pair<const char*, float> m[] = {{"mean", mean[i]}, {"frequency", freq[i]}, {"entropy", entropy[i]}};
+      for (auto& kv : m) {
+        std::ofstream f(measurement_path(c, cells_now, time[i], kv.first, filename));
+        f << rust_f32_to_string(kv.second);
+      }
+    }
+    if (c.dynamics) {
+      std::ofstream f(measurement_path(c, nminus[i] + nplus[i], time[i], "dynamics", filename));
+      const char* names[5] = {"nminus", "nplus", "mean", "variance", "entropy"};
+      f << "{\"dt\":0.1";
+      for (int q = 0; q < 5; ++q) {
+        f << ",\"" << names[q] << "\":[";
+        for (uint32_t j = 0; j < dyn_count[i]; ++j) {
+          if (j) f << ",";
+          f << rust_f32_to_string(dyn[((size_t)i * dyn_points + j) * 5 + q]);
+        }
+        f << "]";
+      }
+      f << "}";
+    }
     if (c.has_subsamples) {                                                           // main.rs:110-123
       SplitMix g{c.seed ^ (idx * 0xD6E8FEB86659FD93ull)};
       for (uint64_t n : c.subsamples) {

@@ -203,6 +203,24 @@ def test_cli_writes_reference_layout(pkg, ctx, tmp_path):
             sub = [p for p in os.listdir(os.path.join(out, "50cells", "ecdna")) if p == t]
             assert sub, "subsample directory missing"
             assert sum(json.load(open(os.path.join(out, "50cells", "ecdna", t, name))).values()) == 50
+    # the optional outputs of the pre-0.19 reference: summaries and dynamics
+    out2 = str(tmp_path / "out2")
+    r = subprocess.run([exe, "--b1", "1.2", "--cells", "300", "--runs", "2", "--summaries", "--dynamics", out2],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    o2 = pkg.SimulationOptions(b1=1.2, cells=300, runs=2)
+    res2 = ctx.run(o2, want=WANT + ("dyn", "dyn_count"), dyn_points=300, dyn_dt=0.1)
+    for i in range(2):
+        t2 = f"{float(res2.time[i]):.1f}".replace(".", "dot") + "years"
+        name2 = f"1b0_1dot2b1_0d0_0d1_{260 + i}idx.json"
+        for what, val in (("mean", res2.mean[i]), ("frequency", res2.frequency[i]), ("entropy", res2.entropy[i])):
+            got = float(open(os.path.join(out2, "300cells", what, t2, name2)).read())
+            assert np.float32(got) == np.float32(val), what
+        dyn = json.load(open(os.path.join(out2, "300cells", "dynamics", t2, name2)))
+        n = int(res2.dyn_count[i])
+        assert len(dyn["nplus"]) == n and dyn["dt"] == 0.1
+        np.testing.assert_array_equal(np.array(dyn["nplus"], dtype=np.float32), res2.dyn[i][:n, 1])
+        np.testing.assert_array_equal(np.array(dyn["mean"], dtype=np.float32), res2.dyn[i][:n, 2])
     # clap-compatible errors
     assert subprocess.run([exe, "--years", "3", "--cells", "4", out], capture_output=True).returncode == 2
     assert subprocess.run([exe], capture_output=True).returncode == 2
