@@ -32,7 +32,7 @@ STOP_NAMES = ["NoIndividualsLeft", "MaxItersReached", "MaxTimeReached", "MaxIndi
               "AbsorbingStateReached", "CopyNumberOverflow", "HistogramOverflow", "ReplayExhausted",
               "ReplayInconsistent"]
 FLAG_HIST_TRUNCATED, FLAG_SPILLED = 0x100, 0x200
-RNG_PHILOX, RNG_REPLAY = 0, 1
+RNG_PHILOX, RNG_REPLAY, RNG_UNIFORMS = 0, 1, 2
 STATE_AUTO, STATE_SMEM, STATE_HBM = 0, 1, 2
 WANT_DIGEST = 0x1
 MAX_ITER = 1_000_000_000  # main.rs:23
@@ -57,7 +57,7 @@ class ParamsT(C.Structure):
         ("abc_thresholds", C.c_float * 4),
         ("state_mode", C.c_uint32), ("tile_width", C.c_uint32), ("smem_bins", C.c_uint32),
         ("max_copies", C.c_uint32), ("hist_stride", C.c_uint32), ("flags", C.c_uint32),
-        ("spill_records", C.c_uint32),
+        ("spill_records", C.c_uint32), ("replay_u64", C.c_void_p),
     ]
 
 
@@ -257,7 +257,7 @@ class Context:
     def make_params(self, opts, n_runs, rates_per_run=None, replay=None, replay_offsets=None, dyn_points=0,
                     dyn_dt=0.1, abc_target=None, abc_thresholds=(0.05, 0.1, 0.1, 0.1), state_mode=STATE_AUTO,
                     tile_width=0, smem_bins=0, max_copies=0, hist_stride=0, digest=False, bd_count_mode=0,
-                    snapshots=True, spill_records=0):
+                    snapshots=True, spill_records=0, replay_u64=None):
         keep = {}
         p = ParamsT()
         p.abi_version = ABI_VERSION
@@ -278,6 +278,9 @@ class Context:
         if replay is not None:
             keep["replay"], keep["replay_off"] = replay, replay_offsets
             p.rng_mode, p.replay, p.replay_offsets = RNG_REPLAY, _addr(replay), _addr(replay_offsets)
+        if replay_u64 is not None:
+            keep["replay_u64"], keep["replay_off"] = replay_u64, replay_offsets
+            p.rng_mode, p.replay_u64, p.replay_offsets = RNG_UNIFORMS, _addr(replay_u64), _addr(replay_offsets)
         p.dyn_points, p.dyn_dt = dyn_points, dyn_dt
         if abc_target is not None:
             keep["abc"] = abc_target

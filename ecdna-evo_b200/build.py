@@ -9,7 +9,10 @@ LIB_PATH = os.path.join(PKG_DIR, "libecdna_b200.so")
 CLI_PATH = os.path.join(PKG_DIR, "host", "ecdna")
 CSRC = os.path.join(PKG_DIR, "csrc")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared",
-              "-Xcompiler", "-fPIC", "-cudart", "static", "-diag-suppress", "128"]
+              "-Xcompiler", "-fPIC", "-cudart", "static", "-diag-suppress", "128",
+              # every fused multiply-add in this library is written explicitly (the CPU oracle is compiled
+              # with -ffp-contract=off and must see the same roundings)
+              "-fmad=false"]
 
 
 def _nvcc():

@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "ssa_kernel.cuh"
+#include "uniform_replay.cuh"
 
 using namespace ecdna;
 
@@ -54,6 +55,7 @@ struct ecdna_b200_ctx {
   bool have_total = false;
   std::string err;
   DevBuf init_k, init_c, snap, rates, replay, replay_off, abc_cdf, arena, counters, scratch, park_list, park_rec,
+      cells, zig,
       cols[C_COUNT];
   size_t arena_words = 0, arena_kcap = 0;
   ecdna_b200_timing_t timing{};
@@ -224,7 +226,12 @@ int validate(ecdna_b200_ctx* ctx, const ecdna_b200_params_t* p, uint64_t n_runs)
   if (p->max_iter == 0 || p->max_iter >= (1ull << 32)) return fail(ctx, ECDNA_B200_ERR_BAD_PARAMS, "max_iter must be in [1, 2^32)");
   if (p->n_init == 0 || !p->init_k || !p->init_c) return fail(ctx, ECDNA_B200_ERR_BAD_PARAMS, "empty initial distribution (ensure!(!distribution.is_empty()), process.rs:88)");
   if (p->n_snapshots && !p->snapshot_cells) return fail(ctx, ECDNA_B200_ERR_BAD_PARAMS, "snapshot_cells is NULL");
-  if (p->rng_mode > 1) return fail(ctx, ECDNA_B200_ERR_BAD_PARAMS, "unknown rng_mode");
+  if (p->rng_mode > 2) return fail(ctx, ECDNA_B200_ERR_BAD_PARAMS, "unknown rng_mode");
+  if (p->rng_mode == ECDNA_B200_RNG_UNIFORMS) {
+    if (!p->replay_u64 || !p->replay_offsets) return fail(ctx, ECDNA_B200_ERR_BAD_PARAMS, "uniform replay needs replay_u64 and replay_offsets");
+    if (p->n_snapshots || p->dyn_points || p->abc_enabled) return fail(ctx, ECDNA_B200_ERR_BAD_PARAMS, "uniform replay has no snapshots, dynamics or ABC epilogue");
+    if (n_runs * (p->max_cells + 2) > (8ull << 30)) return fail(ctx, ECDNA_B200_ERR_BAD_PARAMS, "uniform replay keeps one u16 per cell per replicate: batch too large");
+  }
   if (p->rng_mode == ECDNA_B200_RNG_REPLAY && (!p->replay || !p->replay_offsets)) return fail(ctx, ECDNA_B200_ERR_BAD_PARAMS, "replay mode needs replay and replay_offsets");
   if (p->state_mode > 2) return fail(ctx, ECDNA_B200_ERR_BAD_PARAMS, "unknown state_mode");
   if (p->tile_width != 0 && p->tile_width != 4 && p->tile_width != 8 && p->tile_width != 16 && p->tile_width != 32) return fail(ctx, ECDNA_B200_ERR_BAD_PARAMS, "tile_width must be 4, 8, 16 or 32");
@@ -332,6 +339,7 @@ int run_common(ecdna_b200_ctx* ctx, const ecdna_b200_params_t* p, uint64_t idx_b
       a.rates_per_run = (const float*)ctx->rates.p;
     }
   }
+  const bool uniforms = p->rng_mode == ECDNA_B200_RNG_UNIFORMS;
   const bool replay = p->rng_mode == ECDNA_B200_RNG_REPLAY;
   if (replay) {
     if (device_io) { a.replay = p->replay; a.replay_off = p->replay_offsets; }
@@ -377,7 +385,53 @@ int run_common(ecdna_b200_ctx* ctx, const ecdna_b200_params_t* p, uint64_t idx_b
     a.park_cap = (uint32_t)cap;
   }
 
-  if (L == 32) rc = replay ? launch_all<32, true>(ctx, a, st, p) : launch_all<32, false>(ctx, a, st, p);
+  if (uniforms) {
+    // the reference's own stream on the reference's own state layout: one thread per replicate
+    UrArgs u{};
+    for (int i = 0; i < 4; ++i) u.rate[i] = a.rate[i];
+    u.rates_per_run = a.rates_per_run;
+    u.segregation = a.segregation; u.cells_stop = a.cells_stop; u.max_iter_m1 = a.max_iter_m1; u.max_time = a.max_time;
+    u.n_runs = a.n_runs; u.n_init = a.n_init; u.init_k = a.init_k; u.init_c = a.init_c; u.init_nminus = a.init_nminus;
+    u.hist_stride = a.hist_stride; u.totals = a.totals; u.out = a.out;
+    u.cap = p->max_cells + 2;
+    CU(ctx->cells.ensure((size_t)n_runs * u.cap * sizeof(uint16_t)));
+    u.cells = (uint16_t*)ctx->cells.p;
+    if (device_io) { u.stream = p->replay_u64; u.stream_off = p->replay_offsets; }
+    else {
+      const uint64_t total = p->replay_offsets[n_runs];
+      CU(ctx->replay.ensure((size_t)total * 8 + 16));
+      CU(ctx->replay_off.ensure((n_runs + 1) * 8));
+      CU(cudaMemcpyAsync(ctx->replay.p, p->replay_u64, (size_t)total * 8, cudaMemcpyHostToDevice, st));
+      CU(cudaMemcpyAsync(ctx->replay_off.p, p->replay_offsets, (n_runs + 1) * 8, cudaMemcpyHostToDevice, st));
+      tm.h2d_bytes += total * 8 + (n_runs + 1) * 8;
+      u.stream = (const uint64_t*)ctx->replay.p;
+      u.stream_off = (const uint64_t*)ctx->replay_off.p;
+    }
+    // Exp1 ziggurat tables, regenerated from the published recurrence (Marsaglia & Tsang 2000)
+    std::vector<double> zig(514);
+    {
+      const double R = 7.69711747013104972, v = 3.949659822581572e-3;
+      double* x = zig.data();
+      double* f = zig.data() + 257;
+      x[0] = v / std::exp(-R);
+      x[1] = R;
+      for (int i = 2; i < 256; ++i) x[i] = -std::log(v / x[i - 1] + std::exp(-x[i - 1]));
+      x[256] = 0.0;
+      for (int i = 0; i < 257; ++i) f[i] = std::exp(-x[i]);
+    }
+    CU(ctx->zig.ensure(zig.size() * 8));
+    CU(cudaMemcpyAsync(ctx->zig.p, zig.data(), zig.size() * 8, cudaMemcpyHostToDevice, st));
+    CU(cudaStreamSynchronize(st));  // `zig` is a stack vector
+    u.zig_x = (const double*)ctx->zig.p;
+    u.zig_f = (const double*)ctx->zig.p + 257;
+    CU(cudaEventRecord(ctx->ev_k0, st));
+    uniform_replay_kernel<<<(unsigned)((n_runs + 63) / 64), 64, 0, st>>>(u);
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(ctx->ev_k1, st));
+    tm.kernel_launches = 1; tm.tile_width = 1; tm.grid_blocks = (uint32_t)((n_runs + 63) / 64); tm.block_threads = 64;
+    rc = ECDNA_B200_OK;
+  }
+  else if (L == 32) rc = replay ? launch_all<32, true>(ctx, a, st, p) : launch_all<32, false>(ctx, a, st, p);
   else if (L == 16) rc = replay ? launch_all<16, true>(ctx, a, st, p) : launch_all<16, false>(ctx, a, st, p);
   else if (L == 8) rc = replay ? launch_all<8, true>(ctx, a, st, p) : launch_all<8, false>(ctx, a, st, p);
   else rc = replay ? launch_all<4, true>(ctx, a, st, p) : launch_all<4, false>(ctx, a, st, p);
@@ -496,7 +550,8 @@ void ecdna_b200_destroy(ecdna_b200_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   DevBuf* bufs[] = {&ctx->init_k, &ctx->init_c, &ctx->snap, &ctx->rates, &ctx->replay, &ctx->replay_off,
-                    &ctx->abc_cdf, &ctx->arena, &ctx->counters, &ctx->scratch, &ctx->park_list, &ctx->park_rec};
+                    &ctx->abc_cdf, &ctx->arena, &ctx->counters, &ctx->scratch, &ctx->park_list, &ctx->park_rec,
+                    &ctx->cells, &ctx->zig};
   for (DevBuf* b : bufs) b->release();
   for (auto& b : ctx->cols) b.release();
   cudaEventDestroy(ctx->ev_begin); cudaEventDestroy(ctx->ev_k0); cudaEventDestroy(ctx->ev_k1); cudaEventDestroy(ctx->ev_end);

@@ -62,7 +62,14 @@ enum {
 /* bit set when the replicate's histogram left shared memory for the HBM arena */
 #define ECDNA_B200_FLAG_SPILLED 0x200u
 
-enum { ECDNA_B200_RNG_PHILOX = 0, ECDNA_B200_RNG_REPLAY = 1 };
+enum {
+  ECDNA_B200_RNG_PHILOX = 0,   /* native: Philox4x32-10 keyed (seed, replicate, event) */
+  ECDNA_B200_RNG_REPLAY = 1,   /* decision stream {event, dt, k, k1}: drives the histogram kernel */
+  ECDNA_B200_RNG_UNIFORMS = 2  /* the reference generator's raw u64 stream: re-runs the replicate on the
+                                  reference's own per-cell layout (verification mode, one thread per
+                                  replicate; outputs: stop_reason, nminus, nplus, time, n_events, kmax,
+                                  hash, chain, hist, sum_k, n_div, n_death; no snapshots/dynamics/ABC) */
+};
 enum { ECDNA_B200_STATE_AUTO = 0, ECDNA_B200_STATE_SMEM = 1, ECDNA_B200_STATE_HBM = 2 };
 
 /* ecdna_b200_params_t.flags */
@@ -127,6 +134,9 @@ typedef struct {
   uint32_t flags;       /* ECDNA_B200_WANT_* */
   uint32_t spill_records; /* parked replicates whose state is saved for the HBM launch (others restart);
                              0 = default (32768), 0xFFFFFFFF = none */
+  /* RNG_UNIFORMS: every u64 the reference's ChaCha8Rng (main.rs:57-58) handed out, all runs back to
+     back; replay_offsets[n_runs + 1] then counts u64 */
+  const uint64_t* replay_u64;
 } ecdna_b200_params_t;
 
 /* Per-run outputs.  Every pointer is optional (NULL = not wanted) and caller-owned.

@@ -120,12 +120,22 @@ struct ChaCha8 {
   uint64_t counter = 0, stream = 0;
   uint32_t buf[64];
   int index = 64;  // 4 blocks buffered, refilled when exhausted
+  uint64_t* rec = nullptr;  // optional export of every u64 handed out (what a recording RngCore sees)
+  uint64_t rec_cap = 0, rec_len = 0;
   ChaCha8(uint64_t seed, uint64_t stream_id) : stream(stream_id) { seed_from_u64(seed, key); }
   void refill() {
     for (int b = 0; b < 4; ++b) chacha_block(key, counter + b, stream, 8, buf + 16 * b);
     counter += 4;
   }
   uint64_t next_u64() {
+    const uint64_t v = raw_u64();
+    if (rec) {
+      if (rec_len < rec_cap) rec[rec_len] = v;
+      rec_len++;
+    }
+    return v;
+  }
+  uint64_t raw_u64() {
     if (index < 63) {
       const uint64_t v = ((uint64_t)buf[index + 1] << 32) | buf[index];
       index += 2;
@@ -637,7 +647,13 @@ int orc_run(const orc_opts* o, orc_out* out) {
     uint32_t kmax = 0;
     const uint64_t h0 = init_state(*o, st, kmax, 0);
     out->kmax = kmax;
-    if (o->rng == 0) { RandSource s(o->seed, o->run_idx); return simulate<VectorState, RandSource, false>(*o, *out, st, s, h0); }
+    if (o->rng == 0) {
+      RandSource s(o->seed, o->run_idx);
+      s.g.rec = out->u64_out; s.g.rec_cap = out->u64_cap;
+      const int rc = simulate<VectorState, RandSource, false>(*o, *out, st, s, h0);
+      out->u64_len = s.g.rec_len;
+      return rc;
+    }
     PhiloxSource s(o->seed, o->run_idx);
     return simulate<VectorState, PhiloxSource, false>(*o, *out, st, s, h0);
   }

@@ -109,6 +109,8 @@ typedef struct {
   uint64_t* snap_cells_out;  /* [n_snap] */
   float* snap_time;          /* [n_snap] */
   float* dyn_out;            /* [dyn_points][5]: nminus, nplus, mean, variance, entropy */
+  uint64_t* u64_out;         /* vector state + rng "rand": every u64 the generator handed out, in order */
+  uint64_t u64_cap, u64_len;
 } orc_out;
 
 int orc_run(const orc_opts* o, orc_out* out);

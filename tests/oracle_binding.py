@@ -52,6 +52,7 @@ class Out(C.Structure):
         ("traj_out", C.c_void_p), ("traj_cap", C.c_uint64),
         ("snap_hist", C.c_void_p), ("snap_cells_out", C.c_void_p), ("snap_time", C.c_void_p),
         ("dyn_out", C.c_void_p),
+        ("u64_out", C.c_void_p), ("u64_cap", C.c_uint64), ("u64_len", C.c_uint64),
     ]
 
 
@@ -139,7 +140,7 @@ def make_opts(b0=1.0, b1=1.0, d0=0.0, d1=0.0, segregation=SEG_BINOMIAL, state=ST
     return o
 
 
-def run(opts, hist_cap=4096, trace_cap=0, traj_cap=0):
+def run(opts, hist_cap=4096, trace_cap=0, traj_cap=0, u64_cap=0):
     out = Out()
     r = Result()
     r.hist = np.zeros(hist_cap, dtype=np.uint64)
@@ -150,6 +151,9 @@ def run(opts, hist_cap=4096, trace_cap=0, traj_cap=0):
     if traj_cap:
         r.traj = np.zeros((traj_cap, 4), dtype=np.uint64)
         out.traj_out, out.traj_cap = _ptr(r.traj), traj_cap
+    if u64_cap:
+        r.u64 = np.zeros(u64_cap, dtype=np.uint64)
+        out.u64_out, out.u64_cap = _ptr(r.u64), u64_cap
     if opts.n_snap:
         r.snap_hist = np.zeros((opts.n_snap, hist_cap), dtype=np.uint64)
         r.snap_cells = np.zeros(opts.n_snap, dtype=np.uint64)
@@ -162,8 +166,10 @@ def run(opts, hist_cap=4096, trace_cap=0, traj_cap=0):
     if rc != 0:
         raise RuntimeError(f"orc_run failed: {rc}")
     for f in ("stop_reason", "kmax", "nminus", "nplus", "n_events", "time", "n_snap_taken", "hash", "chain", "sum_k",
-              "n_div", "n_death", "dyn_count", "trace_len"):
+              "n_div", "n_death", "dyn_count", "trace_len", "u64_len"):
         setattr(r, f, getattr(out, f))
+    if u64_cap:
+        r.u64 = r.u64[: min(r.u64_len, u64_cap)]
     if trace_cap:
         r.trace = r.trace[: min(r.trace_len, trace_cap)]
     if traj_cap:

@@ -226,6 +226,38 @@ def test_cli_writes_reference_layout(pkg, ctx, tmp_path):
     assert subprocess.run([exe], capture_output=True).returncode == 2
 
 
+@pytest.mark.parametrize("name", ["neutral", "selection", "birth_death", "no_uneven", "no_nminus", "k50",
+                                  "deterministic", "multi_bin_initial", "extinction", "time_stop"])
+def test_uniform_level_replay_bit_exact(pkg, ctx, name):
+    """rng_mode UNIFORMS: the kernel consumes the raw u64 stream of the reference-layout oracle's
+    ChaCha8 generator and re-runs the replicate on the reference's own per-cell layout.  Same state
+    after every event (chain digest), same final distribution, clock bits and stop reason."""
+    kw = dict(CASES[name])
+    if name == "time_stop":
+        kw = dict(b0=1.0, b1=1.0, years=4)
+    o = pkg.SimulationOptions(runs=5, save_snapshots=False, **kw)
+    streams, refs = [], []
+    for i in range(o.runs):
+        r = ob.run(oracle_opts(o, o.idx_begin + i, state=ob.STATE_VECTOR, rng=ob.RNG_RAND), hist_cap=512,
+                   u64_cap=4_000_000)
+        assert r.u64_len == len(r.u64)
+        streams.append(r.u64)
+        refs.append(r)
+    offsets = np.zeros(o.runs + 1, dtype=np.uint64)
+    offsets[1:] = np.cumsum([len(s) for s in streams])
+    stream = np.concatenate(streams) if offsets[-1] else np.zeros(1, dtype=np.uint64)
+    if o.max_cells > 10 ** 6:  # the per-cell arena is sized by max_cells
+        o.max_cells = int(max(r.nminus + r.nplus for r in refs)) + 8
+    res = ctx.run(o, want=WANT[:12], replay_u64=stream, replay_offsets=offsets)
+    for i, ref in enumerate(refs):
+        assert_run_equal(res, i, ref, 512)
+    # a stream that ends early is reported, not read past
+    cut = ctx.run(o, n_runs=1, want=WANT[:12], replay_u64=streams[0][: len(streams[0]) // 2],
+                  replay_offsets=np.array([0, len(streams[0]) // 2], dtype=np.uint64))
+    if len(streams[0]) > 4:
+        assert int(cut.stop[0]) == pkg.STOP_REPLAY_END and int(cut.n_events[0]) < refs[0].n_events
+
+
 def test_replay_detects_inconsistency(pkg, ctx):
     o = pkg.SimulationOptions(runs=1, cells=200, save_snapshots=False)
     r = _vector_trace(o, o.idx_begin, ob.RNG_RAND)
