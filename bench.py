@@ -344,10 +344,10 @@ def abc_leg(m, ctx, torch, dist, dev, rank, world, draws=16384, cells=100_000):
     rates = ctx.abc_draw_priors(seed=26, idx_begin=idx0, n_runs=draws)
     rates_d = torch.from_numpy(rates).to(dev)
     tgt_d = torch.from_numpy(tgt.astype(np.int64)).to(dev)
-    want = ("stop_reason", "n_events", "abc_distance", "abc_accept", "mean", "frequency", "entropy")
-    rs, t = m.device_results(torch, draws, want, device=dev)
+    want = ("stop_reason", "n_events", "abc_distance", "abc_accept", "mean", "frequency", "entropy", "hist")
+    rs, t = m.device_results(torch, draws, want, hist_stride=512, device=dev)
     stream = torch.cuda.current_stream(dev).cuda_stream
-    kw = dict(rates_per_run=rates_d, abc_target=tgt_d, abc_thresholds=(0.05, 0.1, 0.1, 0.1))
+    kw = dict(rates_per_run=rates_d, abc_target=tgt_d, abc_thresholds=(0.05, 0.1, 0.1, 0.1), hist_stride=512)
     ctx.run_device(opts, draws, idx0, rs, stream=stream, **kw)  # warm-up
     torch.cuda.synchronize(dev)
     if world > 1:
@@ -355,21 +355,16 @@ def abc_leg(m, ctx, torch, dist, dev, rank, world, draws=16384, cells=100_000):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     ctx.run_device(opts, draws, idx0, rs, stream=stream, **kw)
-    # compaction + the one collective of the path
+    # compaction + the one collective of the path: accepted (rates, distances) and their histograms
     acc_idx = torch.empty(draws, dtype=torch.int32, device=dev)
     n_acc = ctx.compact_accepted(t["abc_accept"].data_ptr(), draws, acc_idx.data_ptr(), stream=stream)
     sel = acc_idx[:n_acc].long()
     payload = torch.cat([rates_d[sel], t["abc_distance"][sel]], dim=1) if n_acc else torch.zeros((0, 8), device=dev)
-    total_acc = n_acc
-    if world > 1:
-        counts = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
-        dist.all_gather(counts, torch.tensor([n_acc], dtype=torch.int64, device=dev))
-        mx = int(max(c.item() for c in counts))
-        pad = torch.zeros((mx, 8), device=dev)
-        pad[:n_acc] = payload
-        gathered = [torch.empty_like(pad) for _ in range(world)]
-        dist.all_gather(gathered, pad)
-        total_acc = int(sum(c.item() for c in counts))
+    hists = t["hist"][sel] if n_acc else torch.zeros((0, 512), dtype=torch.int32, device=dev)
+    all_params = m.gather_accepted(torch, dist, payload)
+    all_hists = m.gather_accepted(torch, dist, hists)
+    total_acc = int(all_params.shape[0])
+    assert all_hists.shape[0] == total_acc
     e1.record()
     torch.cuda.synchronize(dev)
     ms = e0.elapsed_time(e1)
