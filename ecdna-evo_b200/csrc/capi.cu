@@ -266,9 +266,9 @@ int run_common(ecdna_b200_ctx* ctx, const ecdna_b200_params_t* p, uint64_t idx_b
   a.dyn_points = p->dyn_points; a.dyn_dt = p->dyn_dt;
   a.flags = p->flags;
   // tile width: sub-warp tiles divide the instructions per event by 32/L but need enough replicates
-  // to keep every SM busy; measured on B200 (profiles/): 4-lane tiles win from ~1.5k replicates up,
+  // to keep every SM busy; measured on B200 (profiles/): 4-lane tiles win from ~1.2k replicates up,
   // below that a replicate per warp has the shortest event latency
-  const uint32_t L = p->tile_width ? p->tile_width : (n_runs >= 1536 ? 4u : 32u);
+  const uint32_t L = p->tile_width ? p->tile_width : (n_runs >= 1200 ? 4u : 32u);
   const uint32_t default_bins = L == 4 ? 256u : 512u;  // 4-lane tiles: 8 replicates per warp window
   a.kcap_s = p->smem_bins ? ((p->smem_bins + 127u) & ~127u) : default_bins;  // bins come in rows of 4 x 32
   a.kcap_g = ((p->max_copies ? p->max_copies : 65535u) + 128u) & ~127u;
