@@ -186,13 +186,15 @@ def main():
     import torch.distributed as dist
     import _pkg
     m = _pkg.load()
-    m.build()
+    if local_rank == 0:
+        m.build()  # no-op when the prebuilt library matches the sources; only one rank may ever compile
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a B200: libecdna_b200.so has no CPU path")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+        dist.barrier()  # the library is in place before any rank loads it
     ctx = m.Context(local_rank)
 
     kw, reps, desc = WORKLOADS[args.workload]
