@@ -295,20 +295,30 @@ def main():
     k_ms = float(np.mean(kernel_ms))
     achieved = (alg_bytes / args.steps) / (k_ms * 1e-3) / 1e9
     traffic = None
+    inst_per_event = None
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload)
         if tj and tj.get("replicates") == reps and last.tile_width == 4:
             traffic = tj["bytes"]
+            inst_per_event = tj.get("warp_inst_per_event")
     except Exception:
         pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": peak_src, "kernel": f"ssa_kernel<{last.tile_width},false>",
                 "kernel_ms_per_launch": k_ms, "alg_bytes_per_launch": alg_bytes / args.steps,
                 "alg_bytes_per_event": alg_bytes / max(events, 1),
-                "issue_slot_note": "the kernel is instruction-issue / latency bound, not HBM bound: see profiles/ "
-                                   "(53 warp-instructions per event, 47% issue utilisation on this launch)",
                 "note": "achieved = SURVEY 8(d) flat-histogram bytes / kernel time; the histogram lives in shared "
-                        "memory, so measured DRAM traffic (roofline.traffic, bytes per launch) is ~0.4 MB"}
+                        "memory, so measured DRAM traffic (roofline.traffic, bytes per launch, from the ncu capture "
+                        "named in profiles/traffic.json) is only the result arrays"}
+    if inst_per_event:
+        # the binding limit of the shared-memory path is the SM issue rate. Instructions per event come
+        # from the committed ncu capture of this very launch; events/s and the SM clock are measured live.
+        sm_hz = (clocks.get("sm_mhz") or 1965.0) * 1e6 if isinstance(clocks, dict) else 1965.0e6
+        issue_peak = 148 * 4 * sm_hz
+        issued = inst_per_event * (events / args.steps) / (k_ms * 1e-3)
+        roofline["issue"] = {"warp_inst_per_event": inst_per_event, "achieved_warp_inst_per_s": issued,
+                             "peak_warp_inst_per_s": issue_peak, "frac": issued / issue_peak,
+                             "source": tj.get("source")}
 
     if rank == 0:
         cpu = None

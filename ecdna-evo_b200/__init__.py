@@ -19,7 +19,7 @@ from .build import LIB_PATH, build  # noqa: F401
 from .shard import gather_accepted, rank_range  # noqa: F401
 from .abc import ABC_FIELDS, abc_rows, write_abc_csv  # noqa: F401
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 EV_BIRTH_NMINUS, EV_BIRTH_NPLUS, EV_DEATH_NMINUS, EV_DEATH_NPLUS = 0, 1, 2, 3
 SEG_DETERMINISTIC, SEG_BINOMIAL_NO_UNEVEN, SEG_BINOMIAL, SEG_BINOMIAL_NO_NMINUS = 0, 1, 2, 3
 SEGREGATION_NAMES = {  # --segregation values, clap_app.rs:232-238
@@ -57,7 +57,7 @@ class ParamsT(C.Structure):
         ("abc_thresholds", C.c_float * 4),
         ("state_mode", C.c_uint32), ("tile_width", C.c_uint32), ("smem_bins", C.c_uint32),
         ("max_copies", C.c_uint32), ("hist_stride", C.c_uint32), ("flags", C.c_uint32),
-        ("spill_records", C.c_uint32), ("replay_u64", C.c_void_p),
+        ("spill_records", C.c_uint32), ("replay_u64", C.c_void_p), ("slice_events", C.c_uint32),
     ]
 
 
@@ -88,7 +88,8 @@ class TimingT(C.Structure):
         ("tile_width", C.c_uint32), ("smem_bins", C.c_uint32), ("grid_blocks", C.c_uint32),
         ("block_threads", C.c_uint32), ("blocks_per_sm", C.c_uint32),
         ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("total_events", C.c_uint64),
-        ("alg_bytes", C.c_uint64), ("n_spilled", C.c_uint32),
+        ("alg_bytes", C.c_uint64), ("n_spilled", C.c_uint32), ("slice_events", C.c_uint32),
+        ("n_slices", C.c_uint64), ("n_idle_spells", C.c_uint64),
     ]
 
     def as_dict(self):
@@ -257,7 +258,7 @@ class Context:
     def make_params(self, opts, n_runs, rates_per_run=None, replay=None, replay_offsets=None, dyn_points=0,
                     dyn_dt=0.1, abc_target=None, abc_thresholds=(0.05, 0.1, 0.1, 0.1), state_mode=STATE_AUTO,
                     tile_width=0, smem_bins=0, max_copies=0, hist_stride=0, digest=False, bd_count_mode=0,
-                    snapshots=True, spill_records=0, replay_u64=None):
+                    snapshots=True, spill_records=0, replay_u64=None, slice_events=0):
         keep = {}
         p = ParamsT()
         p.abi_version = ABI_VERSION
@@ -291,6 +292,7 @@ class Context:
         p.max_copies, p.hist_stride = max_copies, hist_stride
         p.flags = WANT_DIGEST if digest else 0
         p.spill_records = spill_records
+        p.slice_events = slice_events
         p._keep = keep
         return p
 

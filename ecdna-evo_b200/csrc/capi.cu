@@ -55,7 +55,7 @@ struct ecdna_b200_ctx {
   bool have_total = false;
   std::string err;
   DevBuf init_k, init_c, snap, rates, replay, replay_off, abc_cdf, arena, counters, scratch, park_list, park_rec,
-      cells, zig,
+      cells, zig, ts_ring, ts_rec,
       cols[C_COUNT];
   size_t arena_words = 0, arena_kcap = 0;
   ecdna_b200_timing_t timing{};
@@ -74,10 +74,42 @@ int fail(ecdna_b200_ctx* ctx, int code, const std::string& msg) {
       return fail(ctx, ECDNA_B200_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__)); \
   } while (0)
 
+// Relative duration of one event of every resident replicate with w blocks per SM (w warps per
+// scheduler), measured on B200 with the shared-memory kernel (profiles/r01_j_occupancy.md): one warp per
+// scheduler is bound by the latency of the event's dependent chain, from three on by instruction issue.
+double round_cost(int w) {
+  static const double c[] = {0.0, 1.00, 1.15, 1.45, 1.84, 2.26};
+  return w <= 5 ? c[w] : c[5] + 0.45 * (w - 5);
+}
+
+// How many blocks per SM to launch and whether to time-slice.  Without slicing a batch of equal-length
+// replicates (the unfavourable but common case: C1, C2, C5 are pure-birth runs of identical length) runs
+// as full waves plus a last wave at the occupancy its size gives; with slicing n / slots "waves" run on
+// a launch that holds fewer replicates than the batch.
+void plan_launch(uint64_t n, int sm, int bps, int tiles_per_block, uint32_t slice_events, int* w_out, bool* sliced) {
+  *w_out = bps;
+  *sliced = false;
+  const uint64_t per_w = (uint64_t)sm * tiles_per_block;  // replicates one block per SM holds
+  const bool forced = slice_events != 0 && slice_events != 0xFFFFFFFFu;
+  if (slice_events == 0xFFFFFFFFu || (!forced && n >= 4 * per_w * bps)) return;  // many waves: the queue balances them
+  double best = 1e300;
+  for (int w = 1; w <= bps; ++w) {
+    const uint64_t slots = per_w * w;
+    const uint64_t rem = n % slots;
+    const double direct = (double)(n / slots) * round_cost(w) + (rem ? round_cost((int)((rem + per_w - 1) / per_w)) : 0.0);
+    if (!forced && direct < best) { best = direct; *w_out = w; *sliced = false; }
+    if (n > slots) {
+      const double sl = (double)n / (double)slots * round_cost(w) * 1.03;
+      if (sl < best) { best = sl; *w_out = w; *sliced = true; }
+    }
+  }
+  if (forced && !*sliced) *w_out = bps;  // the batch fits one launch at the lowest occupancy: nothing to slice
+}
+
 // one launch of ssa_kernel<L, GLOBAL, REPLAY>; returns the grid used through *grid_out
 template <int L, bool GLOBAL, bool REPLAY, int KG>
 int launch_kernel(ecdna_b200_ctx* ctx, SsaArgs& a, cudaStream_t st, uint64_t max_items, uint32_t* grid_out,
-                  uint32_t* bps_out) {
+                  uint32_t* bps_out, uint32_t slice_events) {
   auto kern = ssa_kernel<L, GLOBAL, REPLAY, KG>;
   const int warps = kBlockThreads / 32;
   const int tiles_per_block = kBlockThreads / L;
@@ -89,9 +121,43 @@ int launch_kernel(ecdna_b200_ctx* ctx, SsaArgs& a, cudaStream_t st, uint64_t max
   if (bps < 1) return fail(ctx, ECDNA_B200_ERR_BAD_PARAMS, "kernel does not fit on an SM");
   if (GLOBAL && bps > 8) bps = 8;  // bounds the arena: one (32 + kcap_g)-word window per resident warp
   const uint64_t need = (max_items + tiles_per_block - 1) / tiles_per_block;
-  uint64_t grid = (uint64_t)ctx->sm_count * bps;
+  int w = bps;
+  bool sliced = false;
+  if (!GLOBAL && !REPLAY) plan_launch(max_items, ctx->sm_count, bps, tiles_per_block, slice_events, &w, &sliced);
+  uint64_t grid = (uint64_t)ctx->sm_count * w;
   if (need < grid) grid = need;
   if (grid == 0) grid = 1;
+  // a launch of few blocks per SM takes the variant compiled without the register cap
+  constexpr bool HAS_LOWOCC = L == 4 && !GLOBAL && !REPLAY;
+  bool lowocc = false;
+  if constexpr (HAS_LOWOCC) {
+    if (grid <= (uint64_t)ctx->sm_count * kLowOccBlocks) {
+      auto kern_lo = ssa_kernel<L, GLOBAL, REPLAY, KG, true>;
+      CU(cudaFuncSetAttribute(kern_lo, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      int bps_lo = 0;
+      CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps_lo, kern_lo, kBlockThreads, smem));
+      lowocc = (uint64_t)ctx->sm_count * bps_lo >= grid;
+    }
+  }
+  a.ts_quantum = 0;
+  if (sliced) {
+    uint32_t q = slice_events ? slice_events : 1024u;
+    uint32_t q2 = 64;
+    while (q2 < q && q2 < (1u << 30)) q2 <<= 1;
+    uint64_t cap = 1024;
+    while (cap < 2 * max_items) cap <<= 1;
+    const size_t rec_words = (size_t)max_items * (kParkHdr + 32u + a.kcap_s);
+    CU(ctx->ts_ring.ensure(cap * 8));
+    CU(ctx->ts_rec.ensure(rec_words * 4));
+    CU(cudaMemsetAsync(ctx->ts_ring.p, 0, cap * 8, st));
+    a.ts_quantum = q2;
+    a.ts_slots = (uint32_t)(grid * tiles_per_block);
+    a.ts_mask = (uint32_t)(cap - 1);
+    a.ts_ring = (unsigned long long*)ctx->ts_ring.p;
+    a.ts_rec = (uint32_t*)ctx->ts_rec.p;
+    a.ts_ctr = (uint32_t*)((char*)ctx->counters.p + 96);
+    ctx->timing.slice_events = q2;
+  }
   if (GLOBAL) {
     const size_t words = (size_t)grid * warps * Tile<32, true>::window_words(a.kcap_g);
     if (words > ctx->arena_words) {
@@ -104,7 +170,12 @@ int launch_kernel(ecdna_b200_ctx* ctx, SsaArgs& a, cudaStream_t st, uint64_t max
     ctx->arena_kcap = a.kcap_g;
     a.arena = (uint32_t*)ctx->arena.p;
   }
-  kern<<<(unsigned)grid, kBlockThreads, smem, st>>>(a);
+  if constexpr (HAS_LOWOCC) {
+    if (lowocc) ssa_kernel<L, GLOBAL, REPLAY, KG, true><<<(unsigned)grid, kBlockThreads, smem, st>>>(a);
+    else kern<<<(unsigned)grid, kBlockThreads, smem, st>>>(a);
+  } else {
+    kern<<<(unsigned)grid, kBlockThreads, smem, st>>>(a);
+  }
   CU(cudaGetLastError());
   *grid_out = (uint32_t)grid;
   *bps_out = (uint32_t)bps;
@@ -120,7 +191,7 @@ int launch_all(ecdna_b200_ctx* ctx, SsaArgs& a, cudaStream_t st, const ecdna_b20
   if (p->state_mode == ECDNA_B200_STATE_HBM) {
     a.park_list = nullptr;
     a.allow_park = 0;
-    int rc = launch_kernel<32, true, REPLAY, 0>(ctx, a, st, a.n_runs, &grid, &bps);
+    int rc = launch_kernel<32, true, REPLAY, 0>(ctx, a, st, a.n_runs, &grid, &bps, 0);
     if (rc) return rc;
     tm.kernel_launches = 1;
     tm.tile_width = 32;
@@ -128,15 +199,15 @@ int launch_all(ecdna_b200_ctx* ctx, SsaArgs& a, cudaStream_t st, const ecdna_b20
     a.allow_park = p->state_mode == ECDNA_B200_STATE_AUTO ? 1u : 0u;
     // the walk over the shared window is unrolled for the two common window sizes
     int rc;
-    if (!REPLAY && a.kcap_s == 256) rc = launch_kernel<L, false, REPLAY, 2>(ctx, a, st, a.n_runs, &grid, &bps);
-    else if (!REPLAY && a.kcap_s == 512) rc = launch_kernel<L, false, REPLAY, 4>(ctx, a, st, a.n_runs, &grid, &bps);
-    else rc = launch_kernel<L, false, REPLAY, 0>(ctx, a, st, a.n_runs, &grid, &bps);
+    if (!REPLAY && a.kcap_s == 256) rc = launch_kernel<L, false, REPLAY, 2>(ctx, a, st, a.n_runs, &grid, &bps, p->slice_events);
+    else if (!REPLAY && a.kcap_s == 512) rc = launch_kernel<L, false, REPLAY, 4>(ctx, a, st, a.n_runs, &grid, &bps, p->slice_events);
+    else rc = launch_kernel<L, false, REPLAY, 0>(ctx, a, st, a.n_runs, &grid, &bps, p->slice_events);
     if (rc) return rc;
     tm.kernel_launches = 1;
     tm.tile_width = L;
     if (a.allow_park) {
       uint32_t g2 = 0, b2 = 0;
-      rc = launch_kernel<32, true, REPLAY, 0>(ctx, a, st, a.n_runs, &g2, &b2);
+      rc = launch_kernel<32, true, REPLAY, 0>(ctx, a, st, a.n_runs, &g2, &b2, 0);
       if (rc) return rc;
       tm.kernel_launches = 2;
     }
@@ -550,7 +621,7 @@ void ecdna_b200_destroy(ecdna_b200_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   DevBuf* bufs[] = {&ctx->init_k, &ctx->init_c, &ctx->snap, &ctx->rates, &ctx->replay, &ctx->replay_off,
-                    &ctx->abc_cdf, &ctx->arena, &ctx->counters, &ctx->scratch, &ctx->park_list, &ctx->park_rec,
+                    &ctx->abc_cdf, &ctx->arena, &ctx->counters, &ctx->scratch, &ctx->park_list, &ctx->park_rec, &ctx->ts_ring, &ctx->ts_rec,
                     &ctx->cells, &ctx->zig};
   for (DevBuf* b : bufs) b->release();
   for (auto& b : ctx->cols) b.release();
@@ -582,8 +653,10 @@ int ecdna_b200_get_timing(ecdna_b200_ctx* ctx, ecdna_b200_timing_t* t) {
     CU(cudaEventSynchronize(ctx->ev_end));
     CU(cudaEventElapsedTime(&ctx->timing.total_ms, ctx->ev_begin, ctx->ev_end));
   }
-  unsigned long long tot[5];
+  unsigned long long tot[7];
   CU(cudaMemcpy(tot, (char*)ctx->counters.p + 16, sizeof tot, cudaMemcpyDeviceToHost));
+  ctx->timing.n_slices = tot[5];
+  ctx->timing.n_idle_spells = tot[6];
   ctx->timing.total_events = tot[0];
   // division = 4K + 24 + 16, death = 4K + 8 + 16, ecDNA- event = 16 bytes
   ctx->timing.alg_bytes = 4ull * tot[1] + 24ull * tot[2] + 8ull * tot[3] + 16ull * tot[0];

@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define ECDNA_B200_ABI_VERSION 1
+#define ECDNA_B200_ABI_VERSION 2
 
 /* status codes returned by every entry point */
 enum {
@@ -137,6 +137,12 @@ typedef struct {
   /* RNG_UNIFORMS: every u64 the reference's ChaCha8Rng (main.rs:57-58) handed out, all runs back to
      back; replay_offsets[n_runs + 1] then counts u64 */
   const uint64_t* replay_u64;
+  /* Time slicing.  A batch that is somewhat larger than the number of replicates the GPU runs at its
+     most efficient occupancy (rayon's for_each over a range that is not a multiple of the worker
+     count, main.rs:221-224) is run with that many tiles; every slice_events events a replicate makes
+     room for the one that waits longest.  Results do not depend on it.  0 = automatic,
+     0xFFFFFFFF = never, otherwise the slice length in events (rounded up to a power of two). */
+  uint32_t slice_events;
 } ecdna_b200_params_t;
 
 /* Per-run outputs.  Every pointer is optional (NULL = not wanted) and caller-owned.
@@ -178,6 +184,9 @@ typedef struct {
   uint64_t total_events;   /* sum of n_events */
   uint64_t alg_bytes;      /* SURVEY 8(d) flat-histogram model summed over all events */
   uint32_t n_spilled;      /* replicates that moved to the HBM arena */
+  uint32_t slice_events;   /* slice length the launch used; 0 = it did not time-slice */
+  uint64_t n_slices;       /* times a replicate made room for another one */
+  uint64_t n_idle_spells;  /* times a tile of a sliced launch found nothing to run and looked again later */
 } ecdna_b200_timing_t;
 
 typedef struct ecdna_b200_ctx ecdna_b200_ctx;

@@ -112,6 +112,75 @@ def test_hbm_state_bit_exact(pkg, ctx, name, mode):
         assert res.timing.kernel_launches == 2
 
 
+SLICE_CASES = {
+    # tile width, replicates (more than the tiles of one block per SM: 148 * 128 / width), case
+    "warp_selection": (32, 700, dict(b0=1.0, b1=1.3, cells=600)),
+    # early extinctions free tiles: whether anyone still waits at a slice boundary depends on timing
+    "warp_bd": (32, 900, dict(b0=1.0, b1=1.2, d0=0.3, d1=0.3, cells=600)),
+    "l4_bd": (4, 6000, dict(b0=1.0, b1=1.2, d0=0.3, d1=0.3, cells=400)),
+    "l4_selection": (4, 5200, dict(b0=1.0, b1=1.5, cells=400)),
+    "l8_no_uneven": (8, 2600, dict(b0=1.0, b1=1.0, cells=500, segregation="binomial-no-uneven")),
+    "l16_k50": (16, 1300, dict(b0=1.0, b1=1.0, cells=500, initial={50: 1})),
+}
+
+
+@pytest.mark.parametrize("digest", [False, True], ids=["straight", "digest"])
+@pytest.mark.parametrize("name", sorted(SLICE_CASES))
+def test_time_slicing_bit_exact(pkg, ctx, name, digest):
+    """A batch larger than the launch holds is time-sliced: every 64 events a replicate saves its state
+    and makes room for the one that waits longest, and is resumed later by whichever tile is free.
+    Every replicate still matches the oracle bit for bit (the draws are keyed by replicate and event)."""
+    tw, runs, case = SLICE_CASES[name]
+    o = pkg.SimulationOptions(runs=runs, save_snapshots=False, **case)
+    res = ctx.run(o, want=WANT, digest=digest, tile_width=tw, slice_events=64)
+    assert res.timing.slice_events == 64
+    if "_bd" not in name:
+        assert res.timing.n_slices > 0
+    for i in range(o.runs):
+        ref = ob.run(oracle_opts(o, o.idx_begin + i), hist_cap=512)
+        assert_run_equal(res, i, ref, 512, digest=digest)
+    assert res.timing.total_events == int(res.n_events.sum())
+
+
+def test_time_slicing_keeps_snapshots_dynamics_and_parking(pkg, ctx):
+    """Snapshot cursor, dynamics cursor and the roofline counters travel with a sliced replicate, and a
+    sliced replicate that outgrows the shared window still moves to the HBM launch."""
+    o = pkg.SimulationOptions(b0=1.0, b1=1.2, d0=0.2, d1=0.2, cells=1500, runs=5000, initial={2: 40, 0: 11},
+                              snapshots=[1, 51, 60, 500, 1000, 1500])
+    want = WANT + ("snap_count", "snap_cells", "snap_time", "snap_hist", "dyn", "dyn_count")
+    kw = dict(want=want, tile_width=4, dyn_points=100, dyn_dt=0.1)
+    a = ctx.run(o, slice_events=0xFFFFFFFF, **kw)
+    b = ctx.run(o, slice_events=128, **kw)
+    assert a.timing.slice_events == 0 and a.timing.n_slices == 0
+    assert b.timing.slice_events == 128 and b.timing.n_slices > 0
+    for f in want:
+        x, y = getattr(a, f), getattr(b, f)
+        if x.dtype.kind == "f":
+            x, y = x.view(np.uint32), y.view(np.uint32)
+        np.testing.assert_array_equal(x, y, err_msg=f)
+    # parking: copy numbers beyond a 128-bin window
+    o2 = pkg.SimulationOptions(runs=700, save_snapshots=False, b0=1.0, b1=1.3, cells=3000, initial={50: 1})
+    c = ctx.run(o2, want=WANT, tile_width=32, smem_bins=128, slice_events=0xFFFFFFFF)
+    d = ctx.run(o2, want=WANT, tile_width=32, smem_bins=128, slice_events=64)
+    assert d.timing.n_slices > 0 and d.timing.n_spilled > 0 and d.timing.kernel_launches == 2
+    for f in ("stop_reason", "nminus", "nplus", "n_events", "kmax", "hist", "sum_k", "n_div", "n_death"):
+        np.testing.assert_array_equal(getattr(c, f), getattr(d, f), err_msg=f)
+    np.testing.assert_array_equal(c.time.view(np.uint32), d.time.view(np.uint32))
+
+
+def test_automatic_slicing_only_where_it_pays(pkg, ctx):
+    """slice_events = 0: small batches and batches of many waves run as before; a batch a little larger
+    than two blocks per SM hold is sliced."""
+    o = pkg.SimulationOptions(b0=1.0, b1=1.5, cells=300, save_snapshots=False)
+    small = ctx.run(o, n_runs=64, want=("n_events",), tile_width=4)
+    assert small.timing.slice_events == 0
+    mid = ctx.run(o, n_runs=10000, want=("n_events",), tile_width=4)
+    assert mid.timing.slice_events > 0 and mid.timing.grid_blocks == 2 * 148
+    ref = ctx.run(o, n_runs=10000, want=("n_events",), tile_width=4, slice_events=0xFFFFFFFF)
+    assert ref.timing.slice_events == 0 and ref.timing.grid_blocks == 313
+    np.testing.assert_array_equal(mid.n_events, ref.n_events)
+
+
 def test_smem_only_mode_reports_overflow(pkg, ctx):
     """state_mode SMEM never parks: a replicate that outgrows the window stops with HIST_OVERFLOW."""
     o = pkg.SimulationOptions(runs=4, save_snapshots=False, **CASES["wide"])
