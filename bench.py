@@ -47,6 +47,8 @@ def parse():
     ap.add_argument("--tile-width", type=int, default=0)
     ap.add_argument("--smem-bins", type=int, default=0)
     ap.add_argument("--state", default="auto", choices=["auto", "smem", "hbm"])
+    ap.add_argument("--slice-events", type=lambda v: int(v, 0), default=0,
+                    help="time-slice length in events (0 = automatic, 0xFFFFFFFF = never)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-abc", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -204,7 +206,8 @@ def main():
     stride = 512
     dyn = dict(dyn_points=300, dyn_dt=0.1) if args.workload == "C3" else {}
     want = WANT + (("dyn", "dyn_count") if dyn else ())
-    knobs = dict(tile_width=args.tile_width, smem_bins=args.smem_bins, state_mode=state_mode, hist_stride=stride, **dyn)
+    knobs = dict(tile_width=args.tile_width, smem_bins=args.smem_bins, state_mode=state_mode, hist_stride=stride,
+                 slice_events=args.slice_events, **dyn)
 
     res_struct, tensors = m.device_results(torch, reps, want + ("sum_k", "n_div", "n_death"),
                                            dyn_points=dyn.get("dyn_points", 0), hist_stride=stride, device=dev)

@@ -25,7 +25,7 @@ stream = torch.cuda.current_stream(dev).cuda_stream
 torch.cuda.synchronize()
 t0 = time.perf_counter()
 ctx.run_device(opts, draws, opts.idx_begin, rs, stream=stream, rates_per_run=rates_d, abc_target=tgt_d,
-               abc_thresholds=(0.05, 0.1, 0.1, 0.1))
+               abc_thresholds=(0.05, 0.1, 0.1, 0.1), slice_events=int(os.environ.get("SLICE", "0"), 0))
 acc_idx = torch.empty(draws, dtype=torch.int32, device=dev)
 n_acc = ctx.compact_accepted(t["abc_accept"].data_ptr(), draws, acc_idx.data_ptr(), stream=stream)
 torch.cuda.synchronize()
@@ -34,6 +34,6 @@ tm = ctx.timing()
 stops = np.bincount(t["stop_reason"].cpu().numpy() & 0xFF, minlength=5)
 post = rates_d[acc_idx[:n_acc].long()].cpu().numpy()
 print(f"draws={draws} wall={dt:.2f}s kernel={tm.kernel_ms/1e3:.2f}s sims/s={draws/dt:.4g} events={tm.total_events:.4g} "
-      f"events/s={tm.total_events/dt:.4g} accepted={n_acc} stops={stops.tolist()} spilled={tm.n_spilled}")
+      f"events/s={tm.total_events/dt:.4g} accepted={n_acc} stops={stops.tolist()} spilled={tm.n_spilled} slice={tm.slice_events} n_slices={tm.n_slices}")
 if n_acc:
     print("posterior mean (b1,d0,d1):", post[:, 1:].mean(axis=0), " truth: 1.4 0.2 0.2")
