@@ -78,8 +78,8 @@ int fail(ecdna_b200_ctx* ctx, int code, const std::string& msg) {
 // scheduler), measured on B200 with the shared-memory kernel (profiles/r01_j_occupancy.md): one warp per
 // scheduler is bound by the latency of the event's dependent chain, from three on by instruction issue.
 double round_cost(int w) {
-  static const double c[] = {0.0, 1.00, 1.15, 1.45, 1.84, 2.26};
-  return w <= 5 ? c[w] : c[5] + 0.45 * (w - 5);
+  static const double c[] = {0.0, 1.00, 1.36, 1.93, 2.52, 3.09};
+  return w <= 5 ? c[w] : c[5] + 0.58 * (w - 5);
 }
 
 // How many blocks per SM to launch and whether to time-slice.  Without slicing a batch of equal-length
