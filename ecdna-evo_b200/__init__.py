@@ -111,7 +111,7 @@ def lib():
         if not os.path.exists(LIB_PATH):
             raise RuntimeError(f"{LIB_PATH} is missing: run __graft_entry__.build() (nvcc, sm_100a). "
                                "There is no CPU fallback.")
-        L = C.CDLL(LIB_PATH)
+        L = C.CDLL(os.environ.get("ECDNA_B200_LIB", LIB_PATH))  # (the override is for A/B experiments)
         L.ecdna_b200_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
         L.ecdna_b200_destroy.argtypes = [C.c_void_p]
         L.ecdna_b200_destroy.restype = None

@@ -6,6 +6,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -86,12 +87,17 @@ double round_cost(int w) {
 // replicates (the unfavourable but common case: C1, C2, C5 are pure-birth runs of identical length) runs
 // as full waves plus a last wave at the occupancy its size gives; with slicing n / slots "waves" run on
 // a launch that holds fewer replicates than the batch.
-void plan_launch(uint64_t n, int sm, int bps, int tiles_per_block, uint32_t slice_events, int* w_out, bool* sliced) {
+void plan_launch(uint64_t n, int sm, int bps, int tiles_per_block, uint32_t slice_events, bool prefer_four, int* w_out,
+                 bool* sliced) {
   *w_out = bps;
   *sliced = false;
   const uint64_t per_w = (uint64_t)sm * tiles_per_block;  // replicates one block per SM holds
   const bool forced = slice_events != 0 && slice_events != 0xFFFFFFFFu;
-  if (slice_events == 0xFFFFFFFFu || (!forced && n >= 4 * per_w * bps)) return;  // many waves: the queue balances them
+  if (slice_events == 0xFFFFFFFFu || (!forced && n >= 4 * per_w * bps)) {  // many waves: the queue balances them
+    // (the 4-lane kernel at 4 blocks per SM and 128 registers is ~4 % ahead of 5 blocks at 96)
+    if (slice_events != 0xFFFFFFFFu && prefer_four && bps > 4) *w_out = 4;
+    return;
+  }
   double best = 1e300;
   for (int w = 1; w <= bps; ++w) {
     const uint64_t slots = per_w * w;
@@ -120,24 +126,26 @@ int launch_kernel(ecdna_b200_ctx* ctx, SsaArgs& a, cudaStream_t st, uint64_t max
   CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, kBlockThreads, smem));
   if (bps < 1) return fail(ctx, ECDNA_B200_ERR_BAD_PARAMS, "kernel does not fit on an SM");
   if (GLOBAL && bps > 8) bps = 8;  // bounds the arena: one (32 + kcap_g)-word window per resident warp
+  if (const char* e = getenv("ECDNA_B200_MAX_BPS")) { const int m = atoi(e); if (m > 0 && m < bps) bps = m; }  // experiments
   const uint64_t need = (max_items + tiles_per_block - 1) / tiles_per_block;
   int w = bps;
   bool sliced = false;
-  if (!GLOBAL && !REPLAY) plan_launch(max_items, ctx->sm_count, bps, tiles_per_block, slice_events, &w, &sliced);
+  if (!GLOBAL && !REPLAY) plan_launch(max_items, ctx->sm_count, bps, tiles_per_block, slice_events, L == 4, &w, &sliced);
   uint64_t grid = (uint64_t)ctx->sm_count * w;
   if (need < grid) grid = need;
   if (grid == 0) grid = 1;
-  // a launch of few blocks per SM takes the variant compiled without the register cap
-  constexpr bool HAS_LOWOCC = L == 4 && !GLOBAL && !REPLAY;
-  bool lowocc = false;
-  if constexpr (HAS_LOWOCC) {
-    if (grid <= (uint64_t)ctx->sm_count * kLowOccBlocks) {
-      auto kern_lo = ssa_kernel<L, GLOBAL, REPLAY, KG, true>;
-      CU(cudaFuncSetAttribute(kern_lo, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      int bps_lo = 0;
-      CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps_lo, kern_lo, kBlockThreads, smem));
-      lowocc = (uint64_t)ctx->sm_count * bps_lo >= grid;
-    }
+  // the build of the kernel that matches the blocks per SM of this launch (see ssa_kernel)
+  constexpr bool HAS_BUILDS = L == 4 && !GLOBAL && !REPLAY;
+  int minb = ECDNA_MIN_BLOCKS_L4;
+  if constexpr (HAS_BUILDS) {
+    const uint64_t per_sm = (grid + ctx->sm_count - 1) / ctx->sm_count;
+    auto fits = [&](auto k, int blocks) -> bool {
+      if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return false;
+      int b = 0;
+      return cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k, kBlockThreads, smem) == cudaSuccess && b >= blocks;
+    };
+    if (per_sm <= 3 && fits(ssa_kernel<L, GLOBAL, REPLAY, KG, 3>, (int)per_sm)) minb = 3;
+    else if (per_sm <= 4 && fits(ssa_kernel<L, GLOBAL, REPLAY, KG, 4>, (int)per_sm)) minb = 4;
   }
   a.ts_quantum = 0;
   if (sliced) {
@@ -170,8 +178,9 @@ int launch_kernel(ecdna_b200_ctx* ctx, SsaArgs& a, cudaStream_t st, uint64_t max
     ctx->arena_kcap = a.kcap_g;
     a.arena = (uint32_t*)ctx->arena.p;
   }
-  if constexpr (HAS_LOWOCC) {
-    if (lowocc) ssa_kernel<L, GLOBAL, REPLAY, KG, true><<<(unsigned)grid, kBlockThreads, smem, st>>>(a);
+  if constexpr (HAS_BUILDS) {
+    if (minb == 3) ssa_kernel<L, GLOBAL, REPLAY, KG, 3><<<(unsigned)grid, kBlockThreads, smem, st>>>(a);
+    else if (minb == 4) ssa_kernel<L, GLOBAL, REPLAY, KG, 4><<<(unsigned)grid, kBlockThreads, smem, st>>>(a);
     else kern<<<(unsigned)grid, kBlockThreads, smem, st>>>(a);
   } else {
     kern<<<(unsigned)grid, kBlockThreads, smem, st>>>(a);
