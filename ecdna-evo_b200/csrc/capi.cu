@@ -345,11 +345,21 @@ int run_common(ecdna_b200_ctx* ctx, const ecdna_b200_params_t* p, uint64_t idx_b
   a.n_runs = (uint32_t)n_runs;
   a.dyn_points = p->dyn_points; a.dyn_dt = p->dyn_dt;
   a.flags = p->flags;
-  // tile width: sub-warp tiles divide the instructions per event by 32/L but need enough replicates
-  // to keep every SM busy; measured on B200 (profiles/): 4-lane tiles win from ~1.2k replicates up,
-  // below that a replicate per warp has the shortest event latency
-  const uint32_t L = p->tile_width ? p->tile_width : (n_runs >= 1200 ? 4u : 32u);
-  const uint32_t default_bins = L == 4 ? 256u : 512u;  // 4-lane tiles: 8 replicates per warp window
+  // tile width: up to one warp per scheduler (4 x 148) an event takes the same time whatever the width
+  // (the latency of its dependent chain, profiles/r01_j_occupancy.md); beyond that the warps share the
+  // issue slots, so take the widest tile that keeps the batch within one warp per scheduler, down to 4
+  // lanes (8 replicates per warp, an eighth of the instructions per event)
+  const uint64_t one_per_scheduler = 4ull * (uint64_t)ctx->sm_count;
+  const uint32_t L = p->tile_width ? p->tile_width
+                     : n_runs <= one_per_scheduler ? 32u
+                     : n_runs <= 2 * one_per_scheduler ? 16u
+                     : n_runs <= 4 * one_per_scheduler ? 8u : 4u;
+  // shared window: 4-lane tiles keep 8 replicates per warp window, so 256 bins unless the initial copy
+  // numbers are large already (they grow to several times the largest initial one)
+  uint32_t k0max = 0;
+  for (uint32_t i = 0; i < p->n_init; ++i)
+    if (p->init_c[i] != 0 && p->init_k[i] > k0max) k0max = p->init_k[i];
+  const uint32_t default_bins = (L == 4 && k0max <= 16u) ? 256u : 512u;
   a.kcap_s = p->smem_bins ? ((p->smem_bins + 127u) & ~127u) : default_bins;  // bins come in rows of 4 x 32
   a.kcap_g = ((p->max_copies ? p->max_copies : 65535u) + 128u) & ~127u;
   if (a.kcap_g < a.kcap_s) a.kcap_g = a.kcap_s;
