@@ -58,23 +58,25 @@ class ParamsT(C.Structure):
         ("state_mode", C.c_uint32), ("tile_width", C.c_uint32), ("smem_bins", C.c_uint32),
         ("max_copies", C.c_uint32), ("hist_stride", C.c_uint32), ("flags", C.c_uint32),
         ("spill_records", C.c_uint32), ("replay_u64", C.c_void_p), ("slice_events", C.c_uint32),
+        ("n_subsamples", C.c_uint32), ("subsample_cells", C.c_void_p),
     ]
 
 
-# (name, dtype, trailing shape as a function of (n_snapshots, dyn_points, hist_stride))
+# (name, dtype, trailing shape as a function of (n_snapshots, dyn_points, hist_stride, n_subsamples))
 RESULT_FIELDS = [
-    ("stop_reason", np.uint32, lambda s, d, h: ()), ("nminus", np.uint64, lambda s, d, h: ()),
-    ("nplus", np.uint64, lambda s, d, h: ()), ("time", np.float32, lambda s, d, h: ()),
-    ("n_events", np.uint64, lambda s, d, h: ()), ("kmax", np.uint32, lambda s, d, h: ()),
-    ("mean", np.float32, lambda s, d, h: ()), ("frequency", np.float32, lambda s, d, h: ()),
-    ("entropy", np.float32, lambda s, d, h: ()), ("variance", np.float32, lambda s, d, h: ()),
-    ("abc_distance", np.float32, lambda s, d, h: (4,)), ("abc_accept", np.uint8, lambda s, d, h: ()),
-    ("hash", np.uint64, lambda s, d, h: ()), ("chain", np.uint64, lambda s, d, h: ()),
-    ("hist", np.uint32, lambda s, d, h: (h,)), ("snap_count", np.uint32, lambda s, d, h: ()),
-    ("snap_cells", np.uint64, lambda s, d, h: (s,)), ("snap_time", np.float32, lambda s, d, h: (s,)),
-    ("snap_hist", np.uint32, lambda s, d, h: (s, h)), ("dyn_count", np.uint32, lambda s, d, h: ()),
-    ("dyn", np.float32, lambda s, d, h: (d, 5)), ("sum_k", np.uint64, lambda s, d, h: ()),
-    ("n_div", np.uint32, lambda s, d, h: ()), ("n_death", np.uint32, lambda s, d, h: ()),
+    ("stop_reason", np.uint32, lambda s, d, h, u: ()), ("nminus", np.uint64, lambda s, d, h, u: ()),
+    ("nplus", np.uint64, lambda s, d, h, u: ()), ("time", np.float32, lambda s, d, h, u: ()),
+    ("n_events", np.uint64, lambda s, d, h, u: ()), ("kmax", np.uint32, lambda s, d, h, u: ()),
+    ("mean", np.float32, lambda s, d, h, u: ()), ("frequency", np.float32, lambda s, d, h, u: ()),
+    ("entropy", np.float32, lambda s, d, h, u: ()), ("variance", np.float32, lambda s, d, h, u: ()),
+    ("abc_distance", np.float32, lambda s, d, h, u: (4,)), ("abc_accept", np.uint8, lambda s, d, h, u: ()),
+    ("hash", np.uint64, lambda s, d, h, u: ()), ("chain", np.uint64, lambda s, d, h, u: ()),
+    ("hist", np.uint32, lambda s, d, h, u: (h,)), ("snap_count", np.uint32, lambda s, d, h, u: ()),
+    ("snap_cells", np.uint64, lambda s, d, h, u: (s,)), ("snap_time", np.float32, lambda s, d, h, u: (s,)),
+    ("snap_hist", np.uint32, lambda s, d, h, u: (s, h)), ("dyn_count", np.uint32, lambda s, d, h, u: ()),
+    ("dyn", np.float32, lambda s, d, h, u: (d, 5)), ("sum_k", np.uint64, lambda s, d, h, u: ()),
+    ("n_div", np.uint32, lambda s, d, h, u: ()), ("n_death", np.uint32, lambda s, d, h, u: ()),
+    ("sub_hist", np.uint32, lambda s, d, h, u: (u, h)),
 ]
 
 
@@ -258,7 +260,7 @@ class Context:
     def make_params(self, opts, n_runs, rates_per_run=None, replay=None, replay_offsets=None, dyn_points=0,
                     dyn_dt=0.1, abc_target=None, abc_thresholds=(0.05, 0.1, 0.1, 0.1), state_mode=STATE_AUTO,
                     tile_width=0, smem_bins=0, max_copies=0, hist_stride=0, digest=False, bd_count_mode=0,
-                    snapshots=True, spill_records=0, replay_u64=None, slice_events=0):
+                    snapshots=True, spill_records=0, replay_u64=None, slice_events=0, subsamples=None):
         keep = {}
         p = ParamsT()
         p.abi_version = ABI_VERSION
@@ -293,6 +295,10 @@ class Context:
         p.flags = WANT_DIGEST if digest else 0
         p.spill_records = spill_records
         p.slice_events = slice_events
+        subs = list(opts.subsamples or []) if subsamples is None else list(subsamples)
+        if subs:  # main.rs:110-123
+            keep["subs"] = np.array(subs, dtype=np.uint64)
+            p.n_subsamples, p.subsample_cells = len(subs), keep["subs"].ctypes.data
         p._keep = keep
         return p
 
@@ -303,7 +309,7 @@ class Context:
         idx_begin = opts.idx_begin if idx_begin is None else idx_begin
         p = self.make_params(opts, n_runs, **kw)
         stride = p.hist_stride or 512
-        res = Results(n_runs, p.n_snapshots, p.dyn_points, stride, want)
+        res = Results(n_runs, p.n_snapshots, p.dyn_points, stride, want, p.n_subsamples)
         self._check(lib().ecdna_b200_run(self._h, C.byref(p), idx_begin, n_runs, C.byref(res.struct)))
         res.timing = self.timing()
         return res
@@ -349,13 +355,13 @@ def _addr(a):
 class Results:
     """Caller-owned host buffers for ecdna_b200_results_t."""
 
-    def __init__(self, n_runs, n_snapshots, dyn_points, hist_stride, want):
+    def __init__(self, n_runs, n_snapshots, dyn_points, hist_stride, want, n_subsamples=0):
         self.struct = ResultsT()
         self.n_runs = n_runs
         for name, dtype, shape in RESULT_FIELDS:
             if name not in want:
                 continue
-            tail = shape(n_snapshots, dyn_points, hist_stride)
+            tail = shape(n_snapshots, dyn_points, hist_stride, n_subsamples)
             if any(t == 0 for t in tail):
                 continue
             arr = np.zeros((n_runs,) + tail, dtype=dtype)
@@ -367,7 +373,7 @@ class Results:
         return self.stop_reason & 0xFF
 
 
-def device_results(torch, n_runs, want, n_snapshots=0, dyn_points=0, hist_stride=512, device="cuda"):
+def device_results(torch, n_runs, want, n_snapshots=0, dyn_points=0, hist_stride=512, device="cuda", n_subsamples=0):
     """Allocate the result columns as torch tensors on the GPU and return (struct, tensors)."""
     tmap = {np.uint32: torch.int32, np.uint64: torch.int64, np.float32: torch.float32, np.uint8: torch.uint8}
     s = ResultsT()
@@ -375,7 +381,7 @@ def device_results(torch, n_runs, want, n_snapshots=0, dyn_points=0, hist_stride
     for name, dtype, shape in RESULT_FIELDS:
         if name not in want:
             continue
-        tail = shape(n_snapshots, dyn_points, hist_stride)
+        tail = shape(n_snapshots, dyn_points, hist_stride, n_subsamples)
         if any(t == 0 for t in tail):
             continue
         t = torch.zeros((n_runs,) + tail, dtype=tmap[dtype], device=device)

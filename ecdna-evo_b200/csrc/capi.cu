@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "ssa_kernel.cuh"
+#include "subsample.cuh"
 #include "uniform_replay.cuh"
 
 using namespace ecdna;
@@ -43,7 +44,7 @@ struct DevBuf {
 enum Col {
   C_STOP, C_NMINUS, C_NPLUS, C_TIME, C_NEVENTS, C_KMAX, C_MEAN, C_FREQ, C_ENT, C_VAR, C_ABCD, C_ABCA, C_HASH,
   C_CHAIN, C_HIST, C_SNAPCOUNT, C_SNAPCELLS, C_SNAPTIME, C_SNAPHIST, C_DYNCOUNT, C_DYN, C_SUMK, C_NDIV, C_NDEATH,
-  C_COUNT
+  C_SUBHIST, C_COUNT
 };
 
 }  // namespace
@@ -56,7 +57,7 @@ struct ecdna_b200_ctx {
   bool have_total = false;
   std::string err;
   DevBuf init_k, init_c, snap, rates, replay, replay_off, abc_cdf, arena, counters, scratch, park_list, park_rec,
-      cells, zig, ts_ring, ts_rec,
+      cells, zig, ts_ring, ts_rec, sub_sizes, hist_tmp,
       cols[C_COUNT];
   size_t arena_words = 0, arena_kcap = 0;
   ecdna_b200_timing_t timing{};
@@ -261,6 +262,7 @@ size_t col_bytes(int c, const ecdna_b200_params_t* p, uint32_t stride) {
     case C_SNAPTIME: return (size_t)p->n_snapshots * 4;
     case C_SNAPHIST: return (size_t)p->n_snapshots * stride * 4;
     case C_DYN: return (size_t)p->dyn_points * 5 * 4;
+    case C_SUBHIST: return (size_t)p->n_subsamples * stride * 4;
   }
   return 0;
 }
@@ -290,6 +292,7 @@ void** col_slot(ecdna_b200_results_t* r, int c) {
     case C_SUMK: return (void**)&r->sum_k;
     case C_NDIV: return (void**)&r->n_div;
     case C_NDEATH: return (void**)&r->n_death;
+    case C_SUBHIST: return (void**)&r->sub_hist;
   }
   return nullptr;
 }
@@ -318,6 +321,8 @@ int validate(ecdna_b200_ctx* ctx, const ecdna_b200_params_t* p, uint64_t n_runs)
   if (p->max_copies > 65535) return fail(ctx, ECDNA_B200_ERR_BAD_PARAMS, "max_copies must be <= 65535 (DNACopy is u16)");
   if (p->abc_enabled && (!p->abc_target_hist || p->abc_target_len == 0)) return fail(ctx, ECDNA_B200_ERR_BAD_PARAMS, "abc_enabled needs a target distribution");
   if (p->dyn_points && !(p->dyn_dt > 0.f)) return fail(ctx, ECDNA_B200_ERR_BAD_PARAMS, "dyn_dt must be > 0");
+  if (p->n_subsamples && !p->subsample_cells) return fail(ctx, ECDNA_B200_ERR_BAD_PARAMS, "subsample_cells is NULL");
+  if (p->n_subsamples > 65535) return fail(ctx, ECDNA_B200_ERR_BAD_PARAMS, "at most 65535 subsample sizes");
   return ECDNA_B200_OK;
 }
 
@@ -459,6 +464,11 @@ int run_common(ecdna_b200_ctx* ctx, const ecdna_b200_params_t* p, uint64_t idx_b
       if (c == C_SNAPCELLS || c == C_SNAPTIME || c == C_SNAPHIST || c == C_DYN) CU(cudaMemsetAsync(*ds, 0, bytes, st));
     }
   }
+  const bool want_sub = p->n_subsamples != 0 && dev.sub_hist != nullptr;
+  if (want_sub && !dev.hist) {  // the samples are drawn from the final distribution: keep one on the device
+    CU(ctx->hist_tmp.ensure((size_t)n_runs * stride * 4));
+    dev.hist = (uint32_t*)ctx->hist_tmp.p;
+  }
   a.out = dev;
   CU(ctx->counters.ensure(128));
   CU(cudaMemsetAsync(ctx->counters.p, 0, 128, st));
@@ -526,6 +536,21 @@ int run_common(ecdna_b200_ctx* ctx, const ecdna_b200_params_t* p, uint64_t idx_b
   else if (L == 8) rc = replay ? launch_all<8, true>(ctx, a, st, p) : launch_all<8, false>(ctx, a, st, p);
   else rc = replay ? launch_all<4, true>(ctx, a, st, p) : launch_all<4, false>(ctx, a, st, p);
   if (rc) return rc;
+
+  if (want_sub) {  // main.rs:110-123, one warp per (replicate, size)
+    CU(ctx->sub_sizes.ensure((size_t)p->n_subsamples * 8));
+    CU(cudaMemcpyAsync(ctx->sub_sizes.p, p->subsample_cells, (size_t)p->n_subsamples * 8, cudaMemcpyHostToDevice, st));
+    tm.h2d_bytes += (size_t)p->n_subsamples * 8;
+    SubArgs sa{};
+    sa.seed_lo = a.seed_lo; sa.seed_hi = a.seed_hi; sa.idx_begin = idx_begin;
+    sa.n_runs = a.n_runs; sa.n_sub = p->n_subsamples; sa.stride = stride;
+    sa.sizes = (const unsigned long long*)ctx->sub_sizes.p;
+    sa.hist = dev.hist; sa.out = dev.sub_hist;
+    const unsigned long long tasks = (unsigned long long)n_runs * p->n_subsamples;
+    subsample_kernel<<<(unsigned)((tasks + 3) / 4), 128, 0, st>>>(sa);
+    CU(cudaGetLastError());
+    tm.kernel_launches += 1;
+  }
 
   if (!device_io) {
     for (int c = 0; c < C_COUNT; ++c) {
@@ -640,7 +665,7 @@ void ecdna_b200_destroy(ecdna_b200_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   DevBuf* bufs[] = {&ctx->init_k, &ctx->init_c, &ctx->snap, &ctx->rates, &ctx->replay, &ctx->replay_off,
-                    &ctx->abc_cdf, &ctx->arena, &ctx->counters, &ctx->scratch, &ctx->park_list, &ctx->park_rec, &ctx->ts_ring, &ctx->ts_rec,
+                    &ctx->abc_cdf, &ctx->arena, &ctx->counters, &ctx->scratch, &ctx->park_list, &ctx->park_rec, &ctx->ts_ring, &ctx->ts_rec, &ctx->sub_sizes, &ctx->hist_tmp,
                     &ctx->cells, &ctx->zig};
   for (DevBuf* b : bufs) b->release();
   for (auto& b : ctx->cols) b.release();

@@ -262,30 +262,6 @@ std::map<uint32_t, uint64_t> load_json_hist(const std::string& path) {
   return out;
 }
 
-// splitmix64 stream for the host-side subsampling (EcDNADistribution::into_subsampled, main.rs:110-123)
-struct SplitMix {
-  uint64_t s;
-  uint64_t next() { uint64_t z = (s += 0x9E3779B97F4A7C15ull); z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull; z = (z ^ (z >> 27)) * 0x94D049BB133111EBull; return z ^ (z >> 31); }
-  uint64_t below(uint64_t n) { const unsigned __int128 m = (unsigned __int128)next() * n; return (uint64_t)(m >> 64); }
-};
-// n cells drawn without replacement from the distribution (multivariate hypergeometric, class by class)
-std::vector<uint32_t> subsample(const uint32_t* hist, uint32_t len, uint64_t n, SplitMix& g) {
-  std::vector<uint32_t> out(len, 0);
-  uint64_t remaining = 0;
-  for (uint32_t k = 0; k < len; ++k) remaining += hist[k];
-  if (n >= remaining) { out.assign(hist, hist + len); return out; }
-  std::vector<uint64_t> left(hist, hist + len);
-  for (uint64_t d = 0; d < n; ++d) {
-    uint64_t r = g.below(remaining);
-    for (uint32_t k = 0; k < len; ++k) {
-      if (r < left[k]) { left[k]--; out[k]++; break; }
-      r -= left[k];
-    }
-    remaining--;
-  }
-  return out;
-}
-
 std::string utc_now() {
   using namespace std::chrono;
   const auto now = system_clock::now();
@@ -367,10 +343,14 @@ int main(int argc, char** argv) {
   p.n_init = (uint32_t)init_k.size(); p.init_k = init_k.data(); p.init_c = init_c.data();
   p.n_snapshots = (uint32_t)snapshots.size(); p.snapshot_cells = snapshots.empty() ? nullptr : snapshots.data();
   p.tile_width = c.tile_width; p.state_mode = c.state_mode;
+  if (c.has_subsamples && !c.subsamples.empty()) {  // main.rs:110-123, drawn on the device
+    p.n_subsamples = (uint32_t)c.subsamples.size();
+    p.subsample_cells = c.subsamples.data();
+  }
   uint32_t stride = 1024;
 
   const uint64_t idx_begin = c.seed * 10;  // main.rs:214
-  std::vector<uint32_t> stop(runs), kmax(runs), snap_count(runs), hist, snap_hist;
+  std::vector<uint32_t> stop(runs), kmax(runs), snap_count(runs), hist, snap_hist, sub_hist;
   std::vector<uint64_t> nminus(runs), nplus(runs), snap_cells(runs * snapshots.size());
   std::vector<float> time(runs), snap_time(runs * snapshots.size());
   const uint32_t dyn_points = c.dynamics ? 300u : 0u;  // CHANGELOG.md:34-36
@@ -382,6 +362,7 @@ int main(int argc, char** argv) {
     p.hist_stride = stride;
     hist.assign((size_t)runs * stride, 0);
     snap_hist.assign((size_t)runs * snapshots.size() * stride, 0);
+    sub_hist.assign((size_t)runs * p.n_subsamples * stride, 0);
     ecdna_b200_results_t r;
     std::memset(&r, 0, sizeof r);
     r.stop_reason = stop.data(); r.nminus = nminus.data(); r.nplus = nplus.data(); r.time = time.data();
@@ -389,6 +370,7 @@ int main(int argc, char** argv) {
     if (!snapshots.empty()) { r.snap_count = snap_count.data(); r.snap_cells = snap_cells.data(); r.snap_time = snap_time.data(); r.snap_hist = snap_hist.data(); }
     if (c.summaries) { r.mean = mean.data(); r.frequency = freq.data(); r.entropy = entropy.data(); }
     if (c.dynamics) { r.dyn = dyn.data(); r.dyn_count = dyn_count.data(); }
+    if (p.n_subsamples) r.sub_hist = sub_hist.data();
     rc = ecdna_b200_run(ctx, &p, idx_begin, runs, &r);
     if (rc != ECDNA_B200_OK) { std::fprintf(stderr, "ecdna_b200_run: %s\n", ecdna_b200_last_error(ctx)); return 101; }
     uint32_t top = 0;
@@ -433,13 +415,8 @@ int main(int argc, char** argv) {
       }
       f << "}";
     }
-    if (c.has_subsamples) {                                                           // main.rs:110-123
-      SplitMix g{c.seed ^ (idx * 0xD6E8FEB86659FD93ull)};
-      for (uint64_t n : c.subsamples) {
-        const std::vector<uint32_t> sub = subsample(hist.data() + (size_t)i * stride, stride, n, g);
-        save(c, filename, time[i], sub.data(), stride, verbosity);
-      }
-    }
+    for (uint32_t j = 0; j < p.n_subsamples; ++j)  // main.rs:110-123: one file per --subsamples size
+      save(c, filename, time[i], sub_hist.data() + ((size_t)i * p.n_subsamples + j) * stride, stride, verbosity);
     if (verbosity > 0)  // main.rs:205-210
       std::printf("stop reason: %s\nnminus, nplus: [\n    %llu,\n    %llu,\n]\ntime: %s\n", kStopNames[code > 8 ? 8 : code],
                   (unsigned long long)nminus[i], (unsigned long long)nplus[i], rust_f32_to_string(time[i]).c_str());

@@ -145,6 +145,11 @@ typedef struct {
      room for the one that waits longest.  Results do not depend on it.  0 = automatic,
      0xFFFFFFFF = never, otherwise the slice length in events (rounded up to a power of two). */
   uint32_t slice_events;
+  /* --subsamples (clap_app.rs, main.rs:110-123): after the final state of every replicate, one
+     sample of subsample_cells[j] cells drawn without replacement from it (a size >= the population
+     gives the population).  At most 65535 sizes; may be NULL/0. */
+  uint32_t n_subsamples;
+  const uint64_t* subsample_cells;
 } ecdna_b200_params_t;
 
 /* Per-run outputs.  Every pointer is optional (NULL = not wanted) and caller-owned.
@@ -174,6 +179,7 @@ typedef struct {
   uint64_t* sum_k;       /* [n]  sum over ecDNA+ events of the live histogram width (roofline) */
   uint32_t* n_div;       /* [n]  ecDNA+ divisions */
   uint32_t* n_death;     /* [n]  ecDNA+ deaths */
+  uint32_t* sub_hist;    /* [n][n_subsamples][hist_stride] the subsampled distributions, [0] = cells without ecDNA */
 } ecdna_b200_results_t;
 
 /* what the last run on a context measured (CUDA events on the context's stream) */

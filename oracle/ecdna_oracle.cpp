@@ -759,6 +759,36 @@ void orc_rand_gen_range(uint64_t seed, uint64_t stream, uint64_t n, uint64_t cou
   ChaCha8 g(seed, stream);
   for (uint64_t i = 0; i < count; ++i) out[i] = g.gen_range(n);
 }
+void orc_subsample(const uint64_t* hist, uint32_t len, uint64_t want, uint64_t seed, uint64_t run_idx, uint32_t j,
+                   uint64_t* out) {
+  uint64_t total = 0;
+  for (uint32_t k = 0; k < len; ++k) { out[k] = hist[k]; total += hist[k]; }
+  if (want >= total) return;
+  const bool remove = want > total - want;  // draw the smaller side
+  const uint64_t draws = remove ? total - want : want;
+  const PhiloxKey key{(uint32_t)seed, (uint32_t)(seed >> 32), (uint32_t)run_idx, (uint32_t)(run_idx >> 32)};
+  std::vector<uint64_t> w(hist, hist + len);
+  for (uint64_t d = 0; d < draws; ++d) {
+    const uint64_t n = total - d;
+    uint64_t u = 0;
+    for (uint32_t attempt = 0;; ++attempt) {  // Lemire's unbiased bounded integer
+      uint32_t x[4];
+      philox_slot(key, (uint32_t)d, 0x40000000u + j + 65536u * (attempt >> 1), x);
+      const uint64_t v = (attempt & 1u) ? (((uint64_t)x[2] << 32) | x[3]) : (((uint64_t)x[0] << 32) | x[1]);
+      const unsigned __int128 m = (unsigned __int128)v * n;
+      u = (uint64_t)(m >> 64);
+      const uint64_t lo = (uint64_t)m;
+      if (lo >= n || attempt >= 25u) break;
+      if (lo >= (0 - n) % n) break;
+    }
+    for (uint32_t k = 0; k < len; ++k) {  // the first class whose cumulative count exceeds u
+      if (u < w[k]) { w[k] -= 1; break; }
+      u -= w[k];
+    }
+  }
+  for (uint32_t k = 0; k < len; ++k) out[k] = remove ? w[k] : hist[k] - w[k];
+}
+
 uint64_t orc_hist_weight(uint32_t k) { return hist_weight(k); }
 
 int orc_segregate(uint32_t rule, uint32_t copies, uint64_t seed, uint64_t* k1, uint64_t* k2, uint32_t* uneven) {

@@ -143,6 +143,11 @@ int orc_apply_event(uint64_t* hist, uint32_t cap, uint32_t event, uint32_t segre
                     uint32_t* k_out, uint32_t* k1_out, uint32_t* k2_out, uint32_t* uneven_out);
 int orc_segregate(uint32_t rule, uint32_t copies, uint64_t seed, uint64_t* k1, uint64_t* k2, uint32_t* uneven);
 uint64_t orc_hist_weight(uint32_t k);
+/* EcDNADistribution::into_subsampled (src/main.rs:110-123) in the library's native mode: `want` cells drawn
+   without replacement from hist[0..len) ([0] = cells without ecDNA), one cell per draw, Philox counter
+   (draw, 0x40000000 + j + 65536*(attempt/2), run_lo, run_hi); see csrc/subsample.cuh.  out[0..len). */
+void orc_subsample(const uint64_t* hist, uint32_t len, uint64_t want, uint64_t seed, uint64_t run_idx, uint32_t j,
+                   uint64_t* out);
 
 #ifdef __cplusplus
 }

@@ -99,6 +99,8 @@ def lib():
         L.orc_segregate.argtypes = [C.c_uint32, C.c_uint32, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),
                                     C.POINTER(C.c_uint32)]
         L.orc_segregate.restype = C.c_int
+        L.orc_subsample.argtypes = [C.c_void_p, C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32, C.c_void_p]
+        L.orc_subsample.restype = None
         L.orc_hist_weight.argtypes = [C.c_uint32]
         L.orc_hist_weight.restype = C.c_uint64
         _lib = L
@@ -197,6 +199,14 @@ def stats(hist):
     m, f, e, v = C.c_float(), C.c_float(), C.c_float(), C.c_float()
     lib().orc_stats(_ptr(h), len(h), C.byref(m), C.byref(f), C.byref(e), C.byref(v))
     return m.value, f.value, e.value, v.value
+
+
+def subsample(hist, want, seed, run_idx, j):
+    """into_subsampled (main.rs:110-123) as the library's native mode defines it."""
+    h = np.ascontiguousarray(hist, dtype=np.uint64)
+    out = np.zeros_like(h)
+    lib().orc_subsample(_ptr(h), len(h), int(want), int(seed), int(run_idx), int(j), _ptr(out))
+    return out
 
 
 def ks_distance(h1, h2):

@@ -56,6 +56,7 @@ def test_struct_layout_matches_ctypes(built, tmp_path):
 int main(void) {
   printf("%zu %zu %zu %zu ", sizeof(ecdna_b200_params_t), sizeof(ecdna_b200_results_t), sizeof(ecdna_b200_timing_t), sizeof(ecdna_b200_replay_event_t));
   printf("%zu %zu %zu %zu %zu ", offsetof(ecdna_b200_params_t, max_cells), offsetof(ecdna_b200_params_t, seed), offsetof(ecdna_b200_params_t, init_k), offsetof(ecdna_b200_params_t, abc_thresholds), offsetof(ecdna_b200_params_t, spill_records));
+  printf("%zu %zu %zu ", offsetof(ecdna_b200_params_t, slice_events), offsetof(ecdna_b200_params_t, subsample_cells), offsetof(ecdna_b200_results_t, sub_hist));
   printf("%zu %zu %zu\\n", offsetof(ecdna_b200_results_t, hist), offsetof(ecdna_b200_timing_t, total_events), offsetof(ecdna_b200_timing_t, n_spilled));
   return 0;
 }''')
@@ -66,6 +67,7 @@ int main(void) {
     P, R, T = built.ParamsT, built.ResultsT, built.TimingT
     want = [C.sizeof(P), C.sizeof(R), C.sizeof(T), built.REPLAY_DTYPE.itemsize,
             P.max_cells.offset, P.seed.offset, P.init_k.offset, P.abc_thresholds.offset, P.spill_records.offset,
+            P.slice_events.offset, P.subsample_cells.offset, R.sub_hist.offset,
             R.hist.offset, T.total_events.offset, T.n_spilled.offset]
     assert got == want
 

@@ -255,8 +255,9 @@ def test_cli_writes_reference_layout(pkg, ctx, tmp_path):
     r = subprocess.run(cmd, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     assert "Starting the simulation" in r.stdout and "End simulation" in r.stdout
-    o = pkg.SimulationOptions(b1=1.5, d0=0.1, d1=0.2, cells=500, runs=3, seed=7, snapshots=[1, 100, 500])
-    res = ctx.run(o, want=WANT + ("snap_count", "snap_cells", "snap_time", "snap_hist"))
+    o = pkg.SimulationOptions(b1=1.5, d0=0.1, d1=0.2, cells=500, runs=3, seed=7, snapshots=[1, 100, 500],
+                              subsamples=[50])
+    res = ctx.run(o, want=WANT + ("snap_count", "snap_cells", "snap_time", "snap_hist", "sub_hist"))
     for i in range(3):
         name = f"1b0_1dot5b1_0dot1d0_0dot2d1_{70 + i}idx.json"
         cells = int(res.nminus[i] + res.nplus[i])
@@ -271,7 +272,9 @@ def test_cli_writes_reference_layout(pkg, ctx, tmp_path):
         if cells > 50:
             sub = [p for p in os.listdir(os.path.join(out, "50cells", "ecdna")) if p == t]
             assert sub, "subsample directory missing"
-            assert sum(json.load(open(os.path.join(out, "50cells", "ecdna", t, name))).values()) == 50
+            got = json.load(open(os.path.join(out, "50cells", "ecdna", t, name)))
+            assert sum(got.values()) == 50
+            assert got == {str(k): int(c) for k, c in enumerate(res.sub_hist[i, 0]) if c}
     # the optional outputs of the pre-0.19 reference: summaries and dynamics
     out2 = str(tmp_path / "out2")
     r = subprocess.run([exe, "--b1", "1.2", "--cells", "300", "--runs", "2", "--summaries", "--dynamics", out2],
@@ -339,6 +342,25 @@ def test_replay_detects_inconsistency(pkg, ctx):
     short = r.trace[:50].copy()
     res = ctx.run(o, want=WANT, replay=short, replay_offsets=np.array([0, 50], dtype=np.uint64))
     assert int(res.stop[0]) == pkg.STOP_REPLAY_END and int(res.n_events[0]) == 50
+
+
+def test_subsamples_match_oracle(pkg, ctx):
+    """main.rs:110-123: the --subsamples draws on the device, one warp per (replicate, size), bit for bit the
+    oracle's exact multivariate hypergeometric draw from the final distribution."""
+    sizes = [0, 1, 50, 700, 1400, 2999, 3000, 5000]
+    o = pkg.SimulationOptions(b0=1.0, b1=1.2, d0=0.2, d1=0.2, cells=3000, runs=9, initial={2: 40, 0: 11},
+                              save_snapshots=False, subsamples=sizes)
+    res = ctx.run(o, want=WANT + ("sub_hist",), hist_stride=256)
+    assert res.sub_hist.shape == (o.runs, len(sizes), 256)
+    for i in range(o.runs):
+        final = res.hist[i].astype(np.uint64)
+        for j, n in enumerate(sizes):
+            ref = ob.subsample(final, n, o.seed, o.idx_begin + i, j)
+            np.testing.assert_array_equal(res.sub_hist[i, j].astype(np.uint64), ref, err_msg=f"run {i} size {n}")
+            assert int(res.sub_hist[i, j].sum()) == min(n, int(final.sum()))
+    # without the final distribution among the outputs the library keeps one on the device for itself
+    only = ctx.run(o, want=("sub_hist",), hist_stride=256)
+    np.testing.assert_array_equal(only.sub_hist, res.sub_hist)
 
 
 def test_snapshots_match_oracle(pkg, ctx):

@@ -163,3 +163,26 @@ def test_event_type_frequencies_and_waiting_time():
     obs = np.bincount(ev, minlength=4)
     assert sps.chisquare(obs, lam / lam.sum() * len(ev)).pvalue > 1e-3
     assert sps.kstest(np.array(dts) * lam.sum(), "expon").pvalue > 1e-3
+
+
+def test_subsample_is_an_exact_multivariate_hypergeometric_draw():
+    """into_subsampled (main.rs:110-123) as the native mode defines it: sizes, bounds, the complement rule,
+    determinism, and class frequencies that follow the population's."""
+    hist = np.array([500, 0, 300, 150, 0, 40, 10], dtype=np.uint64)
+    total = int(hist.sum())
+    for want in (0, 1, 17, 499, 500, 501, 999, total, total + 5):
+        out = ob.subsample(hist, want, seed=26, run_idx=260, j=0)
+        assert int(out.sum()) == min(want, total)
+        assert np.all(out <= hist)
+        np.testing.assert_array_equal(out, ob.subsample(hist, want, seed=26, run_idx=260, j=0))
+    assert np.any(ob.subsample(hist, 100, 26, 260, 0) != ob.subsample(hist, 100, 26, 261, 0))
+    assert np.any(ob.subsample(hist, 100, 26, 260, 0) != ob.subsample(hist, 100, 26, 260, 1))
+    # mean class counts over many replicates: E[out_k] = want * hist_k / total (both sides of the complement rule)
+    for want in (200, 800):
+        acc = np.zeros(len(hist))
+        runs = 400
+        for r in range(runs):
+            acc += ob.subsample(hist, want, 7, 1000 + r, 3)
+        expect = want * hist / total
+        sd = np.sqrt(np.maximum(expect * (1 - hist / total), 1e-9) / runs)
+        assert np.all(np.abs(acc / runs - expect) <= 5 * sd + 1e-9)
