@@ -79,17 +79,20 @@ int fail(ecdna_b200_ctx* ctx, int code, const std::string& msg) {
 // Relative duration of one event of every resident replicate with w blocks per SM (w warps per
 // scheduler), measured on B200 with the shared-memory kernel (profiles/r01_j_occupancy.md): one warp per
 // scheduler is bound by the latency of the event's dependent chain, from three on by instruction issue.
-double round_cost(int w) {
-  static const double c[] = {0.0, 1.00, 1.36, 1.93, 2.52, 3.09};
-  return w <= 5 ? c[w] : c[5] + 0.58 * (w - 5);
+double round_cost(int w, int lanes) {
+  static const double c4[] = {0.0, 1.00, 1.36, 1.93, 2.52, 3.09};  // 4-lane tiles (and wider)
+  static const double c2[] = {0.0, 1.00, 1.45, 2.06, 2.70, 3.35};  // 2-lane tiles (3 blocks per SM fit)
+  const double* c = lanes == 2 ? c2 : c4;
+  return w <= 5 ? c[w] : c[5] + 0.6 * (w - 5);
 }
 
 // How many blocks per SM to launch and whether to time-slice.  Without slicing a batch of equal-length
 // replicates (the unfavourable but common case: C1, C2, C5 are pure-birth runs of identical length) runs
 // as full waves plus a last wave at the occupancy its size gives; with slicing n / slots "waves" run on
 // a launch that holds fewer replicates than the batch.
-void plan_launch(uint64_t n, int sm, int bps, int tiles_per_block, uint32_t slice_events, bool prefer_four, int* w_out,
+void plan_launch(uint64_t n, int sm, int bps, int tiles_per_block, uint32_t slice_events, int lanes, int* w_out,
                  bool* sliced) {
+  const bool prefer_four = lanes == 4;
   *w_out = bps;
   *sliced = false;
   const uint64_t per_w = (uint64_t)sm * tiles_per_block;  // replicates one block per SM holds
@@ -103,10 +106,10 @@ void plan_launch(uint64_t n, int sm, int bps, int tiles_per_block, uint32_t slic
   for (int w = 1; w <= bps; ++w) {
     const uint64_t slots = per_w * w;
     const uint64_t rem = n % slots;
-    const double direct = (double)(n / slots) * round_cost(w) + (rem ? round_cost((int)((rem + per_w - 1) / per_w)) : 0.0);
+    const double direct = (double)(n / slots) * round_cost(w, lanes) + (rem ? round_cost((int)((rem + per_w - 1) / per_w), lanes) : 0.0);
     if (!forced && direct < best) { best = direct; *w_out = w; *sliced = false; }
     if (n > slots) {
-      const double sl = (double)n / (double)slots * round_cost(w) * 1.03;
+      const double sl = (double)n / (double)slots * round_cost(w, lanes) * 1.03;
       if (sl < best) { best = sl; *w_out = w; *sliced = true; }
     }
   }
@@ -131,7 +134,7 @@ int launch_kernel(ecdna_b200_ctx* ctx, SsaArgs& a, cudaStream_t st, uint64_t max
   const uint64_t need = (max_items + tiles_per_block - 1) / tiles_per_block;
   int w = bps;
   bool sliced = false;
-  if (!GLOBAL && !REPLAY) plan_launch(max_items, ctx->sm_count, bps, tiles_per_block, slice_events, L == 4, &w, &sliced);
+  if (!GLOBAL && !REPLAY) plan_launch(max_items, ctx->sm_count, bps, tiles_per_block, slice_events, L, &w, &sliced);
   uint64_t grid = (uint64_t)ctx->sm_count * w;
   if (need < grid) grid = need;
   if (grid == 0) grid = 1;
@@ -317,7 +320,8 @@ int validate(ecdna_b200_ctx* ctx, const ecdna_b200_params_t* p, uint64_t n_runs)
   }
   if (p->rng_mode == ECDNA_B200_RNG_REPLAY && (!p->replay || !p->replay_offsets)) return fail(ctx, ECDNA_B200_ERR_BAD_PARAMS, "replay mode needs replay and replay_offsets");
   if (p->state_mode > 2) return fail(ctx, ECDNA_B200_ERR_BAD_PARAMS, "unknown state_mode");
-  if (p->tile_width != 0 && p->tile_width != 4 && p->tile_width != 8 && p->tile_width != 16 && p->tile_width != 32) return fail(ctx, ECDNA_B200_ERR_BAD_PARAMS, "tile_width must be 4, 8, 16 or 32");
+  if (p->tile_width != 0 && p->tile_width != 2 && p->tile_width != 4 && p->tile_width != 8 && p->tile_width != 16 && p->tile_width != 32) return fail(ctx, ECDNA_B200_ERR_BAD_PARAMS, "tile_width must be 2, 4, 8, 16 or 32");
+  if (p->tile_width == 2 && p->rng_mode != ECDNA_B200_RNG_PHILOX) return fail(ctx, ECDNA_B200_ERR_BAD_PARAMS, "2-lane tiles exist for the native random source only");
   if (p->max_copies > 65535) return fail(ctx, ECDNA_B200_ERR_BAD_PARAMS, "max_copies must be <= 65535 (DNACopy is u16)");
   if (p->abc_enabled && (!p->abc_target_hist || p->abc_target_len == 0)) return fail(ctx, ECDNA_B200_ERR_BAD_PARAMS, "abc_enabled needs a target distribution");
   if (p->dyn_points && !(p->dyn_dt > 0.f)) return fail(ctx, ECDNA_B200_ERR_BAD_PARAMS, "dyn_dt must be > 0");
@@ -354,17 +358,22 @@ int run_common(ecdna_b200_ctx* ctx, const ecdna_b200_params_t* p, uint64_t idx_b
   // (the latency of its dependent chain, profiles/r01_j_occupancy.md); beyond that the warps share the
   // issue slots, so take the widest tile that keeps the batch within one warp per scheduler, down to 4
   // lanes (8 replicates per warp, an eighth of the instructions per event)
+  // ... and 2 lanes (16 replicates per warp, each lane carrying two of the event's four Philox slots: 27
+  // instructions per event against 39) once even 4-lane tiles exceed one warp per scheduler by a fifth
+  // (measured crossover: 4-lane tiles time-sliced on one block per SM against one block of 2-lane tiles)
   const uint64_t one_per_scheduler = 4ull * (uint64_t)ctx->sm_count;
+  const bool native = p->rng_mode == ECDNA_B200_RNG_PHILOX;
   const uint32_t L = p->tile_width ? p->tile_width
                      : n_runs <= one_per_scheduler ? 32u
                      : n_runs <= 2 * one_per_scheduler ? 16u
-                     : n_runs <= 4 * one_per_scheduler ? 8u : 4u;
-  // shared window: 4-lane tiles keep 8 replicates per warp window, so 256 bins unless the initial copy
+                     : n_runs <= 4 * one_per_scheduler ? 8u
+                     : (n_runs <= 8 * one_per_scheduler * 6 / 5 || !native) ? 4u : 2u;
+  // shared window: 4- and 2-lane tiles keep 8 / 16 replicates per warp window, so 256 bins unless the initial copy
   // numbers are large already (they grow to several times the largest initial one)
   uint32_t k0max = 0;
   for (uint32_t i = 0; i < p->n_init; ++i)
     if (p->init_c[i] != 0 && p->init_k[i] > k0max) k0max = p->init_k[i];
-  const uint32_t default_bins = (L == 4 && k0max <= 16u) ? 256u : 512u;
+  const uint32_t default_bins = (L <= 4 && k0max <= 16u) ? 256u : 512u;
   a.kcap_s = p->smem_bins ? ((p->smem_bins + 127u) & ~127u) : default_bins;  // bins come in rows of 4 x 32
   a.kcap_g = ((p->max_copies ? p->max_copies : 65535u) + 128u) & ~127u;
   if (a.kcap_g < a.kcap_s) a.kcap_g = a.kcap_s;
@@ -531,6 +540,7 @@ int run_common(ecdna_b200_ctx* ctx, const ecdna_b200_params_t* p, uint64_t idx_b
     tm.kernel_launches = 1; tm.tile_width = 1; tm.grid_blocks = (uint32_t)((n_runs + 63) / 64); tm.block_threads = 64;
     rc = ECDNA_B200_OK;
   }
+  else if (L == 2) rc = launch_all<2, false>(ctx, a, st, p);
   else if (L == 32) rc = replay ? launch_all<32, true>(ctx, a, st, p) : launch_all<32, false>(ctx, a, st, p);
   else if (L == 16) rc = replay ? launch_all<16, true>(ctx, a, st, p) : launch_all<16, false>(ctx, a, st, p);
   else if (L == 8) rc = replay ? launch_all<8, true>(ctx, a, st, p) : launch_all<8, false>(ctx, a, st, p);

@@ -127,10 +127,11 @@ typedef struct {
 
   /* engine knobs (0 = default) */
   uint32_t state_mode;  /* ECDNA_B200_STATE_* */
-  uint32_t tile_width;  /* lanes per replicate: 32 (a warp), 16, 8 or 4; 0 = the widest tile that keeps the
-                           batch within one warp per SM scheduler (<= 592 replicates: 32 ... > 2368: 4) */
+  uint32_t tile_width;  /* lanes per replicate: 32 (a warp), 16, 8, 4 or 2 (2: native random source only);
+                           0 = the widest tile that keeps the batch within about one warp per SM scheduler
+                           (<= 592 replicates: 32, <= 1184: 16, <= 2368: 8, <= 5683: 4, more: 2) */
   uint32_t smem_bins;   /* histogram bins per replicate held in shared memory (rounded up to 128);
-                           0 = 512, or 256 for 4-lane tiles when the initial copy numbers are <= 16 */
+                           0 = 512, or 256 for 4- and 2-lane tiles when the initial copy numbers are <= 16 */
   uint32_t max_copies;  /* largest copy number the HBM arena holds (<= 65535) */
   uint32_t hist_stride; /* bins per output histogram */
   uint32_t flags;       /* ECDNA_B200_WANT_* */

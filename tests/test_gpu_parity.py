@@ -79,8 +79,8 @@ def test_native_bit_exact(pkg, ctx, name, digest):
     assert res.timing.total_events == int(res.n_events.sum())
 
 
-@pytest.mark.parametrize("tile_width", [4, 8, 16])
-@pytest.mark.parametrize("name", ["selection", "birth_death", "k50", "no_uneven"])
+@pytest.mark.parametrize("tile_width", [2, 4, 8, 16])
+@pytest.mark.parametrize("name", ["selection", "birth_death", "k50", "no_uneven", "multi_bin_initial", "extinction"])
 def test_tile_widths_agree(pkg, ctx, name, tile_width):
     """Sub-warp tiles (several replicates per warp) give the same bits as one warp per replicate."""
     o = pkg.SimulationOptions(runs=37, save_snapshots=False, **CASES[name])
@@ -121,6 +121,8 @@ SLICE_CASES = {
     "l4_selection": (4, 5200, dict(b0=1.0, b1=1.5, cells=400)),
     "l8_no_uneven": (8, 2600, dict(b0=1.0, b1=1.0, cells=500, segregation="binomial-no-uneven")),
     "l16_k50": (16, 1300, dict(b0=1.0, b1=1.0, cells=500, initial={50: 1})),
+    "l2_bd": (2, 10000, dict(b0=1.0, b1=1.3, d0=0.2, d1=0.1, cells=300)),
+    "l2_selection": (2, 9600, dict(b0=1.0, b1=1.5, cells=300)),
 }
 
 
