@@ -301,7 +301,7 @@ def main():
     inst_per_event = None
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload)
-        if tj and tj.get("replicates") == reps and last.tile_width == 4:
+        if tj and tj.get("replicates") == reps and last.tile_width == tj.get("tile_width", 4):
             traffic = tj["bytes"]
             inst_per_event = tj.get("warp_inst_per_event")
     except Exception:
