@@ -183,6 +183,34 @@ def test_automatic_slicing_only_where_it_pays(pkg, ctx):
     np.testing.assert_array_equal(mid.n_events, ref.n_events)
 
 
+def test_randomized_differential_across_tile_widths_and_slicing(pkg, ctx):
+    """Twelve random parameter sets (rates with zeros and extremes, all segregation rules, sparse initial
+    distributions, stop by size or by time): every tile width, with and without time slicing, gives the bits
+    of the one-warp-per-replicate digest run, and a sample of replicates equals the oracle."""
+    rng = np.random.default_rng(20261018)
+    rules = ["binomial", "deterministic", "binomial-no-uneven", "binomial-no-nminus"]
+    for case in range(12):
+        b0, b1 = rng.choice([0.0, 0.5, 1.0, 1.7]), rng.choice([0.8, 1.0, 1.5, 3.0])
+        d0, d1 = rng.choice([0.0, 0.0, 0.2, 0.9]), rng.choice([0.0, 0.0, 0.3, 1.1])
+        init = {int(k): int(c) for k, c in zip(rng.choice(np.arange(1, 70), size=3, replace=False), rng.integers(1, 6, size=3))}
+        if rng.random() < 0.5:
+            init[0] = int(rng.integers(1, 8))
+        kw = dict(b0=float(b0), b1=float(b1), d0=float(d0), d1=float(d1), cells=int(rng.integers(60, 2500)),
+                  segregation=str(rng.choice(rules)), initial=init, seed=int(rng.integers(1, 1000)))
+        if rng.random() < 0.3:  # stop by time instead of size (clap group 'stop')
+            del kw["cells"]
+            kw["years"] = int(rng.integers(1, 6))
+        o = pkg.SimulationOptions(runs=700, save_snapshots=False, **kw)
+        ref = ctx.run(o, want=WANT, digest=True, tile_width=32, slice_events=0xFFFFFFFF)
+        for i in range(0, o.runs, 97):
+            assert_run_equal(ref, i, ob.run(oracle_opts(o, o.idx_begin + i), hist_cap=512), 512, digest=True)
+        for tw, sl in ((2, 0xFFFFFFFF), (4, 0xFFFFFFFF), (8, 64), (16, 0xFFFFFFFF), (32, 64), (2, 0)):
+            got = ctx.run(o, want=WANT, digest=False, tile_width=tw, slice_events=sl)
+            for f in ("stop_reason", "nminus", "nplus", "n_events", "kmax", "hist", "sum_k", "n_div", "n_death"):
+                np.testing.assert_array_equal(getattr(ref, f), getattr(got, f), err_msg=f"case {case} {kw} tile {tw} {f}")
+            np.testing.assert_array_equal(ref.time.view(np.uint32), got.time.view(np.uint32), err_msg=f"case {case} tile {tw}")
+
+
 def test_smem_only_mode_reports_overflow(pkg, ctx):
     """state_mode SMEM never parks: a replicate that outgrows the window stops with HIST_OVERFLOW."""
     o = pkg.SimulationOptions(runs=4, save_snapshots=False, **CASES["wide"])
