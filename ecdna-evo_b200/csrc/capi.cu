@@ -6,7 +6,6 @@
 
 #include <cmath>
 #include <cstdio>
-#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -130,7 +129,6 @@ int launch_kernel(ecdna_b200_ctx* ctx, SsaArgs& a, cudaStream_t st, uint64_t max
   CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, kBlockThreads, smem));
   if (bps < 1) return fail(ctx, ECDNA_B200_ERR_BAD_PARAMS, "kernel does not fit on an SM");
   if (GLOBAL && bps > 8) bps = 8;  // bounds the arena: one (32 + kcap_g)-word window per resident warp
-  if (const char* e = getenv("ECDNA_B200_MAX_BPS")) { const int m = atoi(e); if (m > 0 && m < bps) bps = m; }  // experiments
   const uint64_t need = (max_items + tiles_per_block - 1) / tiles_per_block;
   int w = bps;
   bool sliced = false;
