@@ -79,8 +79,8 @@ int fail(ecdna_b200_ctx* ctx, int code, const std::string& msg) {
 // scheduler), measured on B200 with the shared-memory kernel (profiles/r01_j_occupancy.md): one warp per
 // scheduler is bound by the latency of the event's dependent chain, from three on by instruction issue.
 double round_cost(int w, int lanes) {
-  static const double c4[] = {0.0, 1.00, 1.36, 1.93, 2.52, 3.09};  // 4-lane tiles (and wider)
-  static const double c2[] = {0.0, 1.00, 1.45, 2.06, 2.70, 3.35};  // 2-lane tiles (3 blocks per SM fit)
+  static const double c4[] = {0.0, 1.00, 1.47, 2.05, 2.72, 3.31};  // 4-lane tiles (and wider)
+  static const double c2[] = {0.0, 1.00, 1.43, 2.02, 2.65, 3.30};  // 2-lane tiles (3 blocks per SM fit)
   const double* c = lanes == 2 ? c2 : c4;
   return w <= 5 ? c[w] : c[5] + 0.6 * (w - 5);
 }
@@ -357,7 +357,7 @@ int run_common(ecdna_b200_ctx* ctx, const ecdna_b200_params_t* p, uint64_t idx_b
   // issue slots, so take the widest tile that keeps the batch within one warp per scheduler, down to 4
   // lanes (8 replicates per warp, an eighth of the instructions per event)
   // ... and 2 lanes (16 replicates per warp, each lane carrying two of the event's four Philox slots: 27
-  // instructions per event against 39) once even 4-lane tiles exceed one warp per scheduler by a fifth
+  // instructions per event against 39) once even 4-lane tiles exceed one warp per scheduler by ~30 %
   // (measured crossover: 4-lane tiles time-sliced on one block per SM against one block of 2-lane tiles)
   const uint64_t one_per_scheduler = 4ull * (uint64_t)ctx->sm_count;
   const bool native = p->rng_mode == ECDNA_B200_RNG_PHILOX;
@@ -365,7 +365,7 @@ int run_common(ecdna_b200_ctx* ctx, const ecdna_b200_params_t* p, uint64_t idx_b
                      : n_runs <= one_per_scheduler ? 32u
                      : n_runs <= 2 * one_per_scheduler ? 16u
                      : n_runs <= 4 * one_per_scheduler ? 8u
-                     : (n_runs <= 8 * one_per_scheduler * 6 / 5 || !native) ? 4u : 2u;
+                     : (n_runs <= 8 * one_per_scheduler * 13 / 10 || !native) ? 4u : 2u;
   // shared window: 4- and 2-lane tiles keep 8 / 16 replicates per warp window, so 256 bins unless the initial copy
   // numbers are large already (they grow to several times the largest initial one)
   uint32_t k0max = 0;

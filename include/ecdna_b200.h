@@ -129,7 +129,7 @@ typedef struct {
   uint32_t state_mode;  /* ECDNA_B200_STATE_* */
   uint32_t tile_width;  /* lanes per replicate: 32 (a warp), 16, 8, 4 or 2 (2: native random source only);
                            0 = the widest tile that keeps the batch within about one warp per SM scheduler
-                           (<= 592 replicates: 32, <= 1184: 16, <= 2368: 8, <= 5683: 4, more: 2) */
+                           (<= 592 replicates: 32, <= 1184: 16, <= 2368: 8, <= 6156: 4, more: 2) */
   uint32_t smem_bins;   /* histogram bins per replicate held in shared memory (rounded up to 128);
                            0 = 512, or 256 for 4- and 2-lane tiles when the initial copy numbers are <= 16 */
   uint32_t max_copies;  /* largest copy number the HBM arena holds (<= 65535) */
