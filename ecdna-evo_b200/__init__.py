@@ -101,9 +101,23 @@ class TimingT(C.Structure):
 EXPORTED_SYMBOLS = [
     "ecdna_b200_create", "ecdna_b200_destroy", "ecdna_b200_last_error", "ecdna_b200_abi_version", "ecdna_b200_run",
     "ecdna_b200_run_device", "ecdna_b200_get_timing", "ecdna_b200_abc_draw_priors", "ecdna_b200_compact_accepted",
+    "ecdna_b200_plan",
 ]
 
 _lib = None
+
+
+def plan(n_runs, tile_width=0, slice_events=0, sm_count=148, max_blocks_per_sm=None):
+    """ecdna_b200_plan: (lanes, blocks_per_sm, tiles, sliced) the library would launch a batch with."""
+    out = [C.c_uint32() for _ in range(4)]
+    if max_blocks_per_sm is None:  # what fits on a B200 with the default 256-bin window
+        probe = [C.c_uint32() for _ in range(4)]
+        lib().ecdna_b200_plan(n_runs, tile_width, slice_events, sm_count, 1, *[C.byref(x) for x in probe])
+        max_blocks_per_sm = {2: 3, 4: 5}.get(probe[0].value, 4)
+    rc = lib().ecdna_b200_plan(n_runs, tile_width, slice_events, sm_count, max_blocks_per_sm, *[C.byref(x) for x in out])
+    if rc != 0:
+        raise EcdnaB200Error(f"ecdna_b200_plan: status {rc}")
+    return out[0].value, out[1].value, out[2].value, bool(out[3].value)
 
 
 def lib():
@@ -123,6 +137,7 @@ def lib():
         L.ecdna_b200_run_device.argtypes = [C.c_void_p, C.POINTER(ParamsT), C.c_uint64, C.c_uint64,
                                             C.POINTER(ResultsT), C.c_void_p]
         L.ecdna_b200_get_timing.argtypes = [C.c_void_p, C.POINTER(TimingT)]
+        L.ecdna_b200_plan.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32] + [C.POINTER(C.c_uint32)] * 4
         L.ecdna_b200_abc_draw_priors.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_float,
                                                  C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float),
                                                  C.c_void_p]

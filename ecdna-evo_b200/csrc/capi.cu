@@ -85,6 +85,15 @@ double round_cost(int w, int lanes) {
   return w <= 5 ? c[w] : c[5] + 0.6 * (w - 5);
 }
 
+// the default tile width (see the comment at its use in run_common)
+uint32_t default_tile_width(uint64_t n_runs, int sm_count, bool native) {
+  const uint64_t one_per_scheduler = 4ull * (uint64_t)sm_count;
+  return n_runs <= one_per_scheduler ? 32u
+         : n_runs <= 2 * one_per_scheduler ? 16u
+         : n_runs <= 4 * one_per_scheduler ? 8u
+         : (n_runs <= 8 * one_per_scheduler * 13 / 10 || !native) ? 4u : 2u;
+}
+
 // How many blocks per SM to launch and whether to time-slice.  Without slicing a batch of equal-length
 // replicates (the unfavourable but common case: C1, C2, C5 are pure-birth runs of identical length) runs
 // as full waves plus a last wave at the occupancy its size gives; with slicing n / slots "waves" run on
@@ -359,13 +368,8 @@ int run_common(ecdna_b200_ctx* ctx, const ecdna_b200_params_t* p, uint64_t idx_b
   // ... and 2 lanes (16 replicates per warp, each lane carrying two of the event's four Philox slots: 27
   // instructions per event against 39) once even 4-lane tiles exceed one warp per scheduler by ~30 %
   // (measured crossover: 4-lane tiles time-sliced on one block per SM against one block of 2-lane tiles)
-  const uint64_t one_per_scheduler = 4ull * (uint64_t)ctx->sm_count;
   const bool native = p->rng_mode == ECDNA_B200_RNG_PHILOX;
-  const uint32_t L = p->tile_width ? p->tile_width
-                     : n_runs <= one_per_scheduler ? 32u
-                     : n_runs <= 2 * one_per_scheduler ? 16u
-                     : n_runs <= 4 * one_per_scheduler ? 8u
-                     : (n_runs <= 8 * one_per_scheduler * 13 / 10 || !native) ? 4u : 2u;
+  const uint32_t L = p->tile_width ? p->tile_width : default_tile_width(n_runs, ctx->sm_count, native);
   // shared window: 4- and 2-lane tiles keep 8 / 16 replicates per warp window, so 256 bins unless the initial copy
   // numbers are large already (they grow to several times the largest initial one)
   uint32_t k0max = 0;
@@ -645,6 +649,26 @@ __global__ void compact_scatter(const uint8_t* flag, uint32_t n, const uint32_t*
 extern "C" {
 
 int ecdna_b200_abi_version(void) { return ECDNA_B200_ABI_VERSION; }
+
+int ecdna_b200_plan(uint64_t n_runs, uint32_t tile_width, uint32_t slice_events, uint32_t sm_count, uint32_t max_blocks_per_sm,
+                    uint32_t* lanes, uint32_t* blocks_per_sm, uint32_t* tiles, uint32_t* sliced) {
+  if (n_runs == 0 || sm_count == 0 || max_blocks_per_sm == 0 || !lanes || !blocks_per_sm || !tiles || !sliced)
+    return ECDNA_B200_ERR_BAD_PARAMS;
+  const uint32_t L = tile_width ? tile_width : default_tile_width(n_runs, (int)sm_count, true);
+  if (L != 2 && L != 4 && L != 8 && L != 16 && L != 32) return ECDNA_B200_ERR_BAD_PARAMS;
+  int w = 0;
+  bool sl = false;
+  const int tiles_per_block = kBlockThreads / (int)L;
+  plan_launch(n_runs, (int)sm_count, (int)max_blocks_per_sm, tiles_per_block, slice_events, (int)L, &w, &sl);
+  uint64_t grid = (uint64_t)sm_count * (uint64_t)w;
+  const uint64_t need = (n_runs + tiles_per_block - 1) / tiles_per_block;
+  if (need < grid) grid = need;
+  *lanes = L;
+  *blocks_per_sm = (uint32_t)w;
+  *tiles = (uint32_t)(grid * tiles_per_block);
+  *sliced = sl ? 1u : 0u;
+  return ECDNA_B200_OK;
+}
 
 int ecdna_b200_create(int device, ecdna_b200_ctx** out) {
   if (!out) return ECDNA_B200_ERR_BAD_PARAMS;

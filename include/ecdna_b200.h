@@ -206,6 +206,15 @@ void ecdna_b200_destroy(ecdna_b200_ctx* ctx);
 const char* ecdna_b200_last_error(const ecdna_b200_ctx* ctx);
 int ecdna_b200_abi_version(void);
 
+/* What the library would do with a batch (no GPU needed; the same code run plans its launch with):
+   lanes per replicate, blocks of 128 threads per SM, tiles (replicates resident at once) and whether
+   the launch is time-sliced, for a device with sm_count SMs on which max_blocks_per_sm blocks of the
+   kernel fit (B200: 148 SMs; 5 for 4-lane tiles with 256 bins, 3 for 2-lane tiles).
+   tile_width / slice_events as in ecdna_b200_params_t (0 = automatic). */
+int ecdna_b200_plan(uint64_t n_runs, uint32_t tile_width, uint32_t slice_events, uint32_t sm_count,
+                    uint32_t max_blocks_per_sm, uint32_t* lanes, uint32_t* blocks_per_sm, uint32_t* tiles,
+                    uint32_t* sliced);
+
 /* Replaces main.rs:55-211 for idx in [idx_begin, idx_begin + n_runs).  Host buffers in and out;
    blocking; host<->device copies happen inside. */
 int ecdna_b200_run(ecdna_b200_ctx* ctx, const ecdna_b200_params_t* params, uint64_t idx_begin, uint64_t n_runs,

@@ -86,3 +86,20 @@ def test_no_gpu_means_error_not_fallback(built):
     with pytest.raises(built.EcdnaB200Error) as e:
         built.Context(0)
     assert "status 3" in str(e.value)
+
+
+def test_launch_plan_without_a_gpu(built):
+    """ecdna_b200_plan runs the same planning code as a launch: tile width by batch size, blocks per SM, and
+    time slicing only where a batch does not fill a launch evenly."""
+    assert built.plan(100) == (32, 1, 100, False)                  # C1: one warp per replicate
+    assert built.plan(1000)[0] == 16 and built.plan(2000)[0] == 8  # C5: widest tile within one warp per scheduler
+    assert built.plan(4736) == (4, 1, 4736, False)                 # exactly one block of 4-lane tiles per SM
+    lanes, w, tiles, sliced = built.plan(10_000)                   # C2: 2-lane tiles, one block per SM, sliced
+    assert (lanes, w, tiles, sliced) == (2, 1, 9472, True)
+    assert built.plan(9472, tile_width=2) == (2, 1, 9472, False)   # an exact fit needs no slicing
+    assert built.plan(10_000, tile_width=4) == (4, 2, 9472, True)
+    assert built.plan(10_000, tile_width=4, slice_events=0xFFFFFFFF) == (4, 5, 10_016, False)
+    assert built.plan(1_000_000) == (2, 3, 28_416, False)          # C4: many waves, the queue balances them
+    assert built.plan(16_384) == (2, 2, 16_384, False)
+    with pytest.raises(built.EcdnaB200Error):
+        built.plan(100, tile_width=3)
