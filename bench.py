@@ -363,23 +363,27 @@ def abc_leg(m, ctx, torch, dist, dev, rank, world, draws=16384, cells=100_000):
     rs, t = m.device_results(torch, draws, want, hist_stride=512, device=dev)
     stream = torch.cuda.current_stream(dev).cuda_stream
     kw = dict(rates_per_run=rates_d, abc_target=tgt_d, abc_thresholds=(0.05, 0.1, 0.1, 0.1), hist_stride=512)
-    ctx.run_device(opts, draws, idx0, rs, stream=stream, **kw)  # warm-up
+    acc_idx = torch.empty(draws, dtype=torch.int32, device=dev)
+
+    def one_pass():
+        ctx.run_device(opts, draws, idx0, rs, stream=stream, **kw)
+        # compaction + the one collective of the path: accepted (rates, distances) and their histograms
+        n_acc = ctx.compact_accepted(t["abc_accept"].data_ptr(), draws, acc_idx.data_ptr(), stream=stream)
+        sel = acc_idx[:n_acc].long()
+        payload = torch.cat([rates_d[sel], t["abc_distance"][sel]], dim=1) if n_acc else torch.zeros((0, 8), device=dev)
+        hists = t["hist"][sel] if n_acc else torch.zeros((0, 512), dtype=torch.int32, device=dev)
+        all_params = m.gather_accepted(torch, dist, payload)
+        all_hists = m.gather_accepted(torch, dist, hists)
+        assert all_hists.shape[0] == all_params.shape[0]
+        return int(all_params.shape[0])
+
+    one_pass()  # warm-up of the whole pass (library buffers, torch's indexing kernels, the NCCL communicator)
     torch.cuda.synchronize(dev)
     if world > 1:
         dist.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    ctx.run_device(opts, draws, idx0, rs, stream=stream, **kw)
-    # compaction + the one collective of the path: accepted (rates, distances) and their histograms
-    acc_idx = torch.empty(draws, dtype=torch.int32, device=dev)
-    n_acc = ctx.compact_accepted(t["abc_accept"].data_ptr(), draws, acc_idx.data_ptr(), stream=stream)
-    sel = acc_idx[:n_acc].long()
-    payload = torch.cat([rates_d[sel], t["abc_distance"][sel]], dim=1) if n_acc else torch.zeros((0, 8), device=dev)
-    hists = t["hist"][sel] if n_acc else torch.zeros((0, 512), dtype=torch.int32, device=dev)
-    all_params = m.gather_accepted(torch, dist, payload)
-    all_hists = m.gather_accepted(torch, dist, hists)
-    total_acc = int(all_params.shape[0])
-    assert all_hists.shape[0] == total_acc
+    total_acc = one_pass()
     e1.record()
     torch.cuda.synchronize(dev)
     ms = e0.elapsed_time(e1)
