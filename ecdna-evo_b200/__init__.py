@@ -19,7 +19,7 @@ from .build import LIB_PATH, build  # noqa: F401
 from .shard import gather_accepted, rank_range  # noqa: F401
 from .abc import ABC_FIELDS, abc_rows, write_abc_csv  # noqa: F401
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 EV_BIRTH_NMINUS, EV_BIRTH_NPLUS, EV_DEATH_NMINUS, EV_DEATH_NPLUS = 0, 1, 2, 3
 SEG_DETERMINISTIC, SEG_BINOMIAL_NO_UNEVEN, SEG_BINOMIAL, SEG_BINOMIAL_NO_NMINUS = 0, 1, 2, 3
 SEGREGATION_NAMES = {  # --segregation values, clap_app.rs:232-238
@@ -91,7 +91,7 @@ class TimingT(C.Structure):
         ("block_threads", C.c_uint32), ("blocks_per_sm", C.c_uint32),
         ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("total_events", C.c_uint64),
         ("alg_bytes", C.c_uint64), ("n_spilled", C.c_uint32), ("slice_events", C.c_uint32),
-        ("n_slices", C.c_uint64), ("n_idle_spells", C.c_uint64),
+        ("n_slices", C.c_uint64), ("n_idle_spells", C.c_uint64), ("n_finished", C.c_uint64),
     ]
 
     def as_dict(self):
@@ -113,7 +113,7 @@ def plan(n_runs, tile_width=0, slice_events=0, sm_count=148, max_blocks_per_sm=N
     if max_blocks_per_sm is None:  # what fits on a B200 with the default 256-bin window
         probe = [C.c_uint32() for _ in range(4)]
         lib().ecdna_b200_plan(n_runs, tile_width, slice_events, sm_count, 1, *[C.byref(x) for x in probe])
-        max_blocks_per_sm = {2: 3, 4: 5}.get(probe[0].value, 4)
+        max_blocks_per_sm = {1: 3, 2: 3, 4: 5}.get(probe[0].value, 4)
     rc = lib().ecdna_b200_plan(n_runs, tile_width, slice_events, sm_count, max_blocks_per_sm, *[C.byref(x) for x in out])
     if rc != 0:
         raise EcdnaB200Error(f"ecdna_b200_plan: status {rc}")

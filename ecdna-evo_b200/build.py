@@ -8,11 +8,13 @@ ROOT = os.path.dirname(PKG_DIR)
 LIB_PATH = os.path.join(PKG_DIR, "libecdna_b200.so")
 CLI_PATH = os.path.join(PKG_DIR, "host", "ecdna")
 CSRC = os.path.join(PKG_DIR, "csrc")
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared",
-              "-Xcompiler", "-fPIC", "-cudart", "static", "-diag-suppress", "128",
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-Xcompiler", "-fPIC", "-diag-suppress", "128",
               # every fused multiply-add in this library is written explicitly (the CPU oracle is compiled
               # with -ffp-contract=off and must see the same roundings)
               "-fmad=false"]
+LINK_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-cudart", "static"]
+OBJ_DIR = os.path.join(PKG_DIR, "_obj")
 
 
 def _nvcc():
@@ -48,16 +50,38 @@ def _stamp(target, sources, extra=""):
 def build(force=False, verbose=False):
     """Compile csrc/*.cu into libecdna_b200.so and host/*.cpp into the `ecdna` CLI."""
     srcs = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC))] + [os.path.join(ROOT, "include", "ecdna_b200.h")]
-    flags = " ".join(NVCC_FLAGS)
+    flags = " ".join(NVCC_FLAGS + LINK_FLAGS)
     if force or _stale(LIB_PATH, srcs, flags):
-        cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + [
-            "-o", LIB_PATH, os.path.join(CSRC, "capi.cu")]
+        # one object per translation unit (the kernel is instantiated per tile width in its own .cu), in parallel
+        from concurrent.futures import ThreadPoolExecutor
+        os.makedirs(OBJ_DIR, exist_ok=True)
+        units = [f for f in sorted(os.listdir(CSRC)) if f.endswith(".cu")]
+        headers = [x for x in srcs if not x.endswith(".cu")]
+
+        def compile_unit(u):
+            src, obj = os.path.join(CSRC, u), os.path.join(OBJ_DIR, u[:-3] + ".o")
+            if not force and not _stale(obj, [src] + headers, flags):
+                return u, 0, ""
+            cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, src]
+            r = subprocess.run(cmd, capture_output=True, text=True)
+            if r.returncode == 0:
+                _stamp(obj, [src] + headers, flags)
+            return u, r.returncode, r.stdout + r.stderr
+
+        with ThreadPoolExecutor(max_workers=min(len(units), os.cpu_count() or 1)) as ex:
+            results = list(ex.map(compile_unit, units))
+        bad = [(u, out) for u, rc, out in results if rc != 0]
+        if bad:
+            raise RuntimeError("nvcc failed:\n" + "\n".join(f"== {u}\n{out}" for u, out in bad))
+        if verbose:
+            for u, _, out in results:
+                print("==", u)
+                print(out)
+        cmd = [_nvcc()] + LINK_FLAGS + ["-o", LIB_PATH] + [os.path.join(OBJ_DIR, u[:-3] + ".o") for u in units]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
-            raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
+            raise RuntimeError("nvcc (link) failed:\n" + r.stdout + r.stderr)
         _stamp(LIB_PATH, srcs, flags)
-        if verbose:
-            print(r.stderr)
     host_dir = os.path.join(PKG_DIR, "host")
     host_srcs = [os.path.join(host_dir, f) for f in sorted(os.listdir(host_dir)) if f.endswith((".cpp", ".h"))]
     hdr = [os.path.join(ROOT, "include", "ecdna_b200.h")]

@@ -10,7 +10,7 @@
 #include <string>
 #include <vector>
 
-#include "ssa_kernel.cuh"
+#include "engine.cuh"
 #include "subsample.cuh"
 #include "uniform_replay.cuh"
 
@@ -18,216 +18,37 @@ using namespace ecdna;
 
 namespace {
 
-struct DevBuf {
-  void* p = nullptr;
-  size_t cap = 0;
-  cudaError_t ensure(size_t bytes, bool zero_new = false) {
-    if (bytes <= cap) return cudaSuccess;
-    if (p) cudaFree(p);
-    p = nullptr;
-    cap = 0;
-    cudaError_t e = cudaMalloc(&p, bytes);
-    if (e != cudaSuccess) return e;
-    cap = bytes;
-    if (zero_new) e = cudaMemset(p, 0, bytes);
-    return e;
-  }
-  void release() {
-    if (p) cudaFree(p);
-    p = nullptr;
-    cap = 0;
-  }
-};
-
-// the per-run result columns, in the order of ecdna_b200_results_t
-enum Col {
-  C_STOP, C_NMINUS, C_NPLUS, C_TIME, C_NEVENTS, C_KMAX, C_MEAN, C_FREQ, C_ENT, C_VAR, C_ABCD, C_ABCA, C_HASH,
-  C_CHAIN, C_HIST, C_SNAPCOUNT, C_SNAPCELLS, C_SNAPTIME, C_SNAPHIST, C_DYNCOUNT, C_DYN, C_SUMK, C_NDIV, C_NDEATH,
-  C_SUBHIST, C_COUNT
-};
-
-}  // namespace
-
-struct ecdna_b200_ctx {
-  int device = 0;
-  int sm_count = 0;
-  cudaStream_t stream = nullptr;
-  cudaEvent_t ev_begin = nullptr, ev_k0 = nullptr, ev_k1 = nullptr, ev_end = nullptr;
-  bool have_total = false;
-  std::string err;
-  DevBuf init_k, init_c, snap, rates, replay, replay_off, abc_cdf, arena, counters, scratch, park_list, park_rec,
-      cells, zig, ts_ring, ts_rec, sub_sizes, hist_tmp,
-      cols[C_COUNT];
-  size_t arena_words = 0, arena_kcap = 0;
-  ecdna_b200_timing_t timing{};
-};
-
-namespace {
-
-int fail(ecdna_b200_ctx* ctx, int code, const std::string& msg) {
-  if (ctx) ctx->err = msg;
-  return code;
-}
-#define CU(call)                                                                                  \
-  do {                                                                                            \
-    cudaError_t e__ = (call);                                                                     \
-    if (e__ != cudaSuccess)                                                                       \
-      return fail(ctx, ECDNA_B200_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__)); \
-  } while (0)
-
-// Relative duration of one event of every resident replicate with w blocks per SM (w warps per
-// scheduler), measured on B200 with the shared-memory kernel (profiles/r01_j_occupancy.md): one warp per
-// scheduler is bound by the latency of the event's dependent chain, from three on by instruction issue.
-double round_cost(int w, int lanes) {
-  static const double c4[] = {0.0, 1.00, 1.47, 2.05, 2.72, 3.31};  // 4-lane tiles (and wider)
-  static const double c2[] = {0.0, 1.00, 1.43, 2.02, 2.65, 3.30};  // 2-lane tiles (3 blocks per SM fit)
-  const double* c = lanes == 2 ? c2 : c4;
-  return w <= 5 ? c[w] : c[5] + 0.6 * (w - 5);
-}
-
-// the default tile width (see the comment at its use in run_common)
-uint32_t default_tile_width(uint64_t n_runs, int sm_count, bool native) {
-  const uint64_t one_per_scheduler = 4ull * (uint64_t)sm_count;
-  return n_runs <= one_per_scheduler ? 32u
-         : n_runs <= 2 * one_per_scheduler ? 16u
-         : n_runs <= 4 * one_per_scheduler ? 8u
-         : (n_runs <= 8 * one_per_scheduler * 13 / 10 || !native) ? 4u : 2u;
-}
-
-// How many blocks per SM to launch and whether to time-slice.  Without slicing a batch of equal-length
-// replicates (the unfavourable but common case: C1, C2, C5 are pure-birth runs of identical length) runs
-// as full waves plus a last wave at the occupancy its size gives; with slicing n / slots "waves" run on
-// a launch that holds fewer replicates than the batch.
-void plan_launch(uint64_t n, int sm, int bps, int tiles_per_block, uint32_t slice_events, int lanes, int* w_out,
-                 bool* sliced) {
-  const bool prefer_four = lanes == 4;
-  *w_out = bps;
-  *sliced = false;
-  const uint64_t per_w = (uint64_t)sm * tiles_per_block;  // replicates one block per SM holds
-  const bool forced = slice_events != 0 && slice_events != 0xFFFFFFFFu;
-  if (slice_events == 0xFFFFFFFFu || (!forced && n >= 4 * per_w * bps)) {  // many waves: the queue balances them
-    // (the 4-lane kernel at 4 blocks per SM and 128 registers is ~4 % ahead of 5 blocks at 96)
-    if (slice_events != 0xFFFFFFFFu && prefer_four && bps > 4) *w_out = 4;
-    return;
-  }
-  double best = 1e300;
-  for (int w = 1; w <= bps; ++w) {
-    const uint64_t slots = per_w * w;
-    const uint64_t rem = n % slots;
-    const double direct = (double)(n / slots) * round_cost(w, lanes) + (rem ? round_cost((int)((rem + per_w - 1) / per_w), lanes) : 0.0);
-    if (!forced && direct < best) { best = direct; *w_out = w; *sliced = false; }
-    if (n > slots) {
-      const double sl = (double)n / (double)slots * round_cost(w, lanes) * 1.03;
-      if (sl < best) { best = sl; *w_out = w; *sliced = true; }
-    }
-  }
-  if (forced && !*sliced) *w_out = bps;  // the batch fits one launch at the lowest occupancy: nothing to slice
-}
-
-// one launch of ssa_kernel<L, GLOBAL, REPLAY>; returns the grid used through *grid_out
-template <int L, bool GLOBAL, bool REPLAY, int KG>
-int launch_kernel(ecdna_b200_ctx* ctx, SsaArgs& a, cudaStream_t st, uint64_t max_items, uint32_t* grid_out,
-                  uint32_t* bps_out, uint32_t slice_events) {
-  auto kern = ssa_kernel<L, GLOBAL, REPLAY, KG>;
-  const int warps = kBlockThreads / 32;
-  const int tiles_per_block = kBlockThreads / L;
-  const size_t smem = GLOBAL ? 0 : (size_t)warps * Tile<L, GLOBAL>::window_words(a.kcap_s) * sizeof(uint32_t);
-  if (smem > 220 * 1024) return fail(ctx, ECDNA_B200_ERR_BAD_PARAMS, "smem_bins too large for this tile width");
-  CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int bps = 0;
-  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, kBlockThreads, smem));
-  if (bps < 1) return fail(ctx, ECDNA_B200_ERR_BAD_PARAMS, "kernel does not fit on an SM");
-  if (GLOBAL && bps > 8) bps = 8;  // bounds the arena: one (32 + kcap_g)-word window per resident warp
-  const uint64_t need = (max_items + tiles_per_block - 1) / tiles_per_block;
-  int w = bps;
-  bool sliced = false;
-  if (!GLOBAL && !REPLAY) plan_launch(max_items, ctx->sm_count, bps, tiles_per_block, slice_events, L, &w, &sliced);
-  uint64_t grid = (uint64_t)ctx->sm_count * w;
-  if (need < grid) grid = need;
-  if (grid == 0) grid = 1;
-  // the build of the kernel that matches the blocks per SM of this launch (see ssa_kernel)
-  constexpr bool HAS_BUILDS = L == 4 && !GLOBAL && !REPLAY;
-  int minb = ECDNA_MIN_BLOCKS_L4;
-  if constexpr (HAS_BUILDS) {
-    const uint64_t per_sm = (grid + ctx->sm_count - 1) / ctx->sm_count;
-    auto fits = [&](auto k, int blocks) -> bool {
-      if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return false;
-      int b = 0;
-      return cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k, kBlockThreads, smem) == cudaSuccess && b >= blocks;
-    };
-    if (per_sm <= 3 && fits(ssa_kernel<L, GLOBAL, REPLAY, KG, 3>, (int)per_sm)) minb = 3;
-    else if (per_sm <= 4 && fits(ssa_kernel<L, GLOBAL, REPLAY, KG, 4>, (int)per_sm)) minb = 4;
-  }
-  a.ts_quantum = 0;
-  if (sliced) {
-    uint32_t q = slice_events ? slice_events : 1024u;
-    uint32_t q2 = 64;
-    while (q2 < q && q2 < (1u << 30)) q2 <<= 1;
-    uint64_t cap = 1024;
-    while (cap < 2 * max_items) cap <<= 1;
-    const size_t rec_words = (size_t)max_items * (kParkHdr + 32u + a.kcap_s);
-    CU(ctx->ts_ring.ensure(cap * 8));
-    CU(ctx->ts_rec.ensure(rec_words * 4));
-    CU(cudaMemsetAsync(ctx->ts_ring.p, 0, cap * 8, st));
-    a.ts_quantum = q2;
-    a.ts_slots = (uint32_t)(grid * tiles_per_block);
-    a.ts_mask = (uint32_t)(cap - 1);
-    a.ts_ring = (unsigned long long*)ctx->ts_ring.p;
-    a.ts_rec = (uint32_t*)ctx->ts_rec.p;
-    a.ts_ctr = (uint32_t*)((char*)ctx->counters.p + 96);
-    ctx->timing.slice_events = q2;
-  }
-  if (GLOBAL) {
-    const size_t words = (size_t)grid * warps * Tile<32, true>::window_words(a.kcap_g);
-    if (words > ctx->arena_words) {
-      CU(ctx->arena.ensure(words * sizeof(uint32_t)));
-      ctx->arena_words = words;
-      CU(cudaMemsetAsync(ctx->arena.p, 0, words * sizeof(uint32_t), st));
-    } else if (a.kcap_g != ctx->arena_kcap) {
-      CU(cudaMemsetAsync(ctx->arena.p, 0, ctx->arena_words * sizeof(uint32_t), st));
-    }
-    ctx->arena_kcap = a.kcap_g;
-    a.arena = (uint32_t*)ctx->arena.p;
-  }
-  if constexpr (HAS_BUILDS) {
-    if (minb == 3) ssa_kernel<L, GLOBAL, REPLAY, KG, 3><<<(unsigned)grid, kBlockThreads, smem, st>>>(a);
-    else if (minb == 4) ssa_kernel<L, GLOBAL, REPLAY, KG, 4><<<(unsigned)grid, kBlockThreads, smem, st>>>(a);
-    else kern<<<(unsigned)grid, kBlockThreads, smem, st>>>(a);
-  } else {
-    kern<<<(unsigned)grid, kBlockThreads, smem, st>>>(a);
-  }
-  CU(cudaGetLastError());
-  *grid_out = (uint32_t)grid;
-  *bps_out = (uint32_t)bps;
-  return ECDNA_B200_OK;
-}
-
 // phase 1: histogram in shared memory, tiles of L lanes; phase 2: parked replicates, histogram in HBM
-template <int L, bool REPLAY>
-int launch_all(ecdna_b200_ctx* ctx, SsaArgs& a, cudaStream_t st, const ecdna_b200_params_t* p) {
+int launch_all(ecdna_b200_ctx* ctx, SsaArgs& a, cudaStream_t st, const ecdna_b200_params_t* p, uint32_t L, bool replay) {
   uint32_t grid = 0, bps = 0;
   ecdna_b200_timing_t& tm = ctx->timing;
   CU(cudaEventRecord(ctx->ev_k0, st));
   if (p->state_mode == ECDNA_B200_STATE_HBM) {
     a.park_list = nullptr;
     a.allow_park = 0;
-    int rc = launch_kernel<32, true, REPLAY, 0>(ctx, a, st, a.n_runs, &grid, &bps, 0);
+    int rc = launch_hbm(ctx, a, st, replay, &grid, &bps);
     if (rc) return rc;
     tm.kernel_launches = 1;
     tm.tile_width = 32;
+    tm.block_threads = kBlockThreads;
   } else {
     a.allow_park = p->state_mode == ECDNA_B200_STATE_AUTO ? 1u : 0u;
-    // the walk over the shared window is unrolled for the two common window sizes
     int rc;
-    if (!REPLAY && a.kcap_s == 256) rc = launch_kernel<L, false, REPLAY, 2>(ctx, a, st, a.n_runs, &grid, &bps, p->slice_events);
-    else if (!REPLAY && a.kcap_s == 512) rc = launch_kernel<L, false, REPLAY, 4>(ctx, a, st, a.n_runs, &grid, &bps, p->slice_events);
-    else rc = launch_kernel<L, false, REPLAY, 0>(ctx, a, st, a.n_runs, &grid, &bps, p->slice_events);
+    switch (L) {
+      case 1: rc = launch_smem<1>(ctx, a, st, replay, p->slice_events, &grid, &bps); break;
+      case 2: rc = launch_smem<2>(ctx, a, st, replay, p->slice_events, &grid, &bps); break;
+      case 4: rc = launch_smem<4>(ctx, a, st, replay, p->slice_events, &grid, &bps); break;
+      case 8: rc = launch_smem<8>(ctx, a, st, replay, p->slice_events, &grid, &bps); break;
+      case 16: rc = launch_smem<16>(ctx, a, st, replay, p->slice_events, &grid, &bps); break;
+      default: rc = launch_smem<32>(ctx, a, st, replay, p->slice_events, &grid, &bps); break;
+    }
     if (rc) return rc;
     tm.kernel_launches = 1;
     tm.tile_width = L;
+    tm.block_threads = L == 1 ? (uint32_t)block_threads<1>() : (uint32_t)kBlockThreads;
     if (a.allow_park) {
       uint32_t g2 = 0, b2 = 0;
-      rc = launch_kernel<32, true, REPLAY, 0>(ctx, a, st, a.n_runs, &g2, &b2, 0);
+      rc = launch_hbm(ctx, a, st, replay, &g2, &b2);
       if (rc) return rc;
       tm.kernel_launches = 2;
     }
@@ -235,7 +56,6 @@ int launch_all(ecdna_b200_ctx* ctx, SsaArgs& a, cudaStream_t st, const ecdna_b20
   CU(cudaEventRecord(ctx->ev_k1, st));
   tm.smem_bins = a.kcap_s;
   tm.grid_blocks = grid;
-  tm.block_threads = kBlockThreads;
   tm.blocks_per_sm = bps;
   return ECDNA_B200_OK;
 }
@@ -327,8 +147,11 @@ int validate(ecdna_b200_ctx* ctx, const ecdna_b200_params_t* p, uint64_t n_runs)
   }
   if (p->rng_mode == ECDNA_B200_RNG_REPLAY && (!p->replay || !p->replay_offsets)) return fail(ctx, ECDNA_B200_ERR_BAD_PARAMS, "replay mode needs replay and replay_offsets");
   if (p->state_mode > 2) return fail(ctx, ECDNA_B200_ERR_BAD_PARAMS, "unknown state_mode");
-  if (p->tile_width != 0 && p->tile_width != 2 && p->tile_width != 4 && p->tile_width != 8 && p->tile_width != 16 && p->tile_width != 32) return fail(ctx, ECDNA_B200_ERR_BAD_PARAMS, "tile_width must be 2, 4, 8, 16 or 32");
-  if (p->tile_width == 2 && p->rng_mode != ECDNA_B200_RNG_PHILOX) return fail(ctx, ECDNA_B200_ERR_BAD_PARAMS, "2-lane tiles exist for the native random source only");
+  if (p->tile_width != 0 && p->tile_width != 1 && p->tile_width != 2 && p->tile_width != 4 && p->tile_width != 8 && p->tile_width != 16 && p->tile_width != 32) return fail(ctx, ECDNA_B200_ERR_BAD_PARAMS, "tile_width must be 1, 2, 4, 8, 16 or 32");
+  if ((p->tile_width == 1 || p->tile_width == 2) && p->rng_mode != ECDNA_B200_RNG_PHILOX) return fail(ctx, ECDNA_B200_ERR_BAD_PARAMS, "1- and 2-lane tiles exist for the native random source only");
+  if (p->bd_count_mode > 1) return fail(ctx, ECDNA_B200_ERR_BAD_PARAMS, "bd_count_mode must be 0 or 1");
+  if (p->bd_count_mode == 1 && p->rates_per_run && !(p->d0 > 0.f || p->d1 > 0.f))
+    return fail(ctx, ECDNA_B200_ERR_BAD_PARAMS, "bd_count_mode 1 with per-run rates: the BASE d0/d1 select the process type (clap_app.rs:165-174); set one of them > 0 for the birth-death process");
   if (p->max_copies > 65535) return fail(ctx, ECDNA_B200_ERR_BAD_PARAMS, "max_copies must be <= 65535 (DNACopy is u16)");
   if (p->abc_enabled && (!p->abc_target_hist || p->abc_target_len == 0)) return fail(ctx, ECDNA_B200_ERR_BAD_PARAMS, "abc_enabled needs a target distribution");
   if (p->dyn_points && !(p->dyn_dt > 0.f)) return fail(ctx, ECDNA_B200_ERR_BAD_PARAMS, "dyn_dt must be > 0");
@@ -369,12 +192,15 @@ int run_common(ecdna_b200_ctx* ctx, const ecdna_b200_params_t* p, uint64_t idx_b
   // instructions per event against 39) once even 4-lane tiles exceed one warp per scheduler by ~30 %
   // (measured crossover: 4-lane tiles time-sliced on one block per SM against one block of 2-lane tiles)
   const bool native = p->rng_mode == ECDNA_B200_RNG_PHILOX;
-  const uint32_t L = p->tile_width ? p->tile_width : default_tile_width(n_runs, ctx->sm_count, native);
-  // shared window: 4- and 2-lane tiles keep 8 / 16 replicates per warp window, so 256 bins unless the initial copy
-  // numbers are large already (they grow to several times the largest initial one)
+  // shared window: 4-, 2- and 1-lane tiles keep 8 / 16 / 32 replicates per warp window, so 256 bins unless the
+  // initial copy numbers are large already (they grow to several times the largest initial one)
   uint32_t k0max = 0;
   for (uint32_t i = 0; i < p->n_init; ++i)
     if (p->init_c[i] != 0 && p->init_k[i] > k0max) k0max = p->init_k[i];
+  // (1-lane tiles draw 128 segregation bits per event inline and fit six warps per SM with a 256-bin window only)
+  const bool lane_ok = native && k0max <= 16u && (p->smem_bins == 0 || p->smem_bins <= 256u) &&
+                       p->state_mode != ECDNA_B200_STATE_HBM;
+  const uint32_t L = p->tile_width ? p->tile_width : default_tile_width(n_runs, ctx->sm_count, native, lane_ok);
   const uint32_t default_bins = (L <= 4 && k0max <= 16u) ? 256u : 512u;
   a.kcap_s = p->smem_bins ? ((p->smem_bins + 127u) & ~127u) : default_bins;  // bins come in rows of 4 x 32
   a.kcap_g = ((p->max_copies ? p->max_copies : 65535u) + 128u) & ~127u;
@@ -396,6 +222,13 @@ int run_common(ecdna_b200_ctx* ctx, const ecdna_b200_params_t* p, uint64_t idx_b
     ic.push_back((uint32_t)p->init_c[i]);
   }
   if (ik.empty() && nminus0 == 0) return fail(ctx, ECDNA_B200_ERR_BAD_PARAMS, "empty initial distribution (ensure!(!distribution.is_empty()), process.rs:88)");
+  {
+    uint64_t total0 = nminus0;
+    for (uint32_t c : ic) total0 += c;
+    if (nminus0 >= (1ull << 32) || total0 >= (1ull << 32)) return fail(ctx, ECDNA_B200_ERR_BAD_PARAMS, "initial population must be below 2^32 cells");
+    if (p->rng_mode == ECDNA_B200_RNG_UNIFORMS && total0 - nminus0 > p->max_cells + 2)
+      return fail(ctx, ECDNA_B200_ERR_BAD_PARAMS, "uniform replay keeps max_cells + 2 cells per replicate: the initial ecDNA+ population does not fit");
+  }
   a.n_init = (uint32_t)ik.size();
   a.init_nminus = (uint32_t)nminus0;
   if (a.n_init) {
@@ -472,7 +305,8 @@ int run_common(ecdna_b200_ctx* ctx, const ecdna_b200_params_t* p, uint64_t idx_b
       if (bytes == 0) { *ds = nullptr; continue; }
       CU(ctx->cols[c].ensure(bytes));
       *ds = ctx->cols[c].p;
-      if (c == C_SNAPCELLS || c == C_SNAPTIME || c == C_SNAPHIST || c == C_DYN) CU(cudaMemsetAsync(*ds, 0, bytes, st));
+      // (the staging buffers are reused between calls: nothing of an earlier batch may survive)
+      CU(cudaMemsetAsync(*ds, 0, bytes, st));
     }
   }
   const bool want_sub = p->n_subsamples != 0 && dev.sub_hist != nullptr;
@@ -485,7 +319,8 @@ int run_common(ecdna_b200_ctx* ctx, const ecdna_b200_params_t* p, uint64_t idx_b
   CU(cudaMemsetAsync(ctx->counters.p, 0, 128, st));
   a.work_counter = (uint32_t*)ctx->counters.p;                              // [0], [1]: the two queues
   a.park_count = (uint32_t*)ctx->counters.p + 2;
-  a.totals = (unsigned long long*)((char*)ctx->counters.p + 16);
+  a.totals = (unsigned long long*)((char*)ctx->counters.p + kTotalsOffset);
+  ctx->expect_finished = n_runs;
   if (p->state_mode == ECDNA_B200_STATE_AUTO) {
     uint64_t cap = p->spill_records == 0xFFFFFFFFu ? 0 : (p->spill_records ? p->spill_records : 32768u);
     if (cap > n_runs) cap = n_runs;
@@ -542,11 +377,7 @@ int run_common(ecdna_b200_ctx* ctx, const ecdna_b200_params_t* p, uint64_t idx_b
     tm.kernel_launches = 1; tm.tile_width = 1; tm.grid_blocks = (uint32_t)((n_runs + 63) / 64); tm.block_threads = 64;
     rc = ECDNA_B200_OK;
   }
-  else if (L == 2) rc = launch_all<2, false>(ctx, a, st, p);
-  else if (L == 32) rc = replay ? launch_all<32, true>(ctx, a, st, p) : launch_all<32, false>(ctx, a, st, p);
-  else if (L == 16) rc = replay ? launch_all<16, true>(ctx, a, st, p) : launch_all<16, false>(ctx, a, st, p);
-  else if (L == 8) rc = replay ? launch_all<8, true>(ctx, a, st, p) : launch_all<8, false>(ctx, a, st, p);
-  else rc = replay ? launch_all<4, true>(ctx, a, st, p) : launch_all<4, false>(ctx, a, st, p);
+  else rc = launch_all(ctx, a, st, p, L, replay);
   if (rc) return rc;
 
   if (want_sub) {  // main.rs:110-123, one warp per (replicate, size)
@@ -575,6 +406,11 @@ int run_common(ecdna_b200_ctx* ctx, const ecdna_b200_params_t* p, uint64_t idx_b
     }
     CU(cudaEventRecord(ctx->ev_end, st));
     CU(cudaStreamSynchronize(st));
+    // every replicate of the batch must have gone through the epilogue (a lost one would leave zeros behind)
+    unsigned long long fin = 0;
+    CU(cudaMemcpy(&fin, (char*)ctx->counters.p + kTotalsOffset + 7 * 8, 8, cudaMemcpyDeviceToHost));
+    if (fin != n_runs)
+      return fail(ctx, ECDNA_B200_ERR_INTERNAL, "internal error: " + std::to_string(fin) + " of " + std::to_string(n_runs) + " replicates finished");
   }
   return ECDNA_B200_OK;
 }
@@ -654,11 +490,11 @@ int ecdna_b200_plan(uint64_t n_runs, uint32_t tile_width, uint32_t slice_events,
                     uint32_t* lanes, uint32_t* blocks_per_sm, uint32_t* tiles, uint32_t* sliced) {
   if (n_runs == 0 || sm_count == 0 || max_blocks_per_sm == 0 || !lanes || !blocks_per_sm || !tiles || !sliced)
     return ECDNA_B200_ERR_BAD_PARAMS;
-  const uint32_t L = tile_width ? tile_width : default_tile_width(n_runs, (int)sm_count, true);
-  if (L != 2 && L != 4 && L != 8 && L != 16 && L != 32) return ECDNA_B200_ERR_BAD_PARAMS;
+  const uint32_t L = tile_width ? tile_width : default_tile_width(n_runs, (int)sm_count, true, true);
+  if (L != 1 && L != 2 && L != 4 && L != 8 && L != 16 && L != 32) return ECDNA_B200_ERR_BAD_PARAMS;
   int w = 0;
   bool sl = false;
-  const int tiles_per_block = kBlockThreads / (int)L;
+  const int tiles_per_block = (L == 1 ? block_threads<1>() : kBlockThreads) / (int)L;
   plan_launch(n_runs, (int)sm_count, (int)max_blocks_per_sm, tiles_per_block, slice_events, (int)L, &w, &sl);
   uint64_t grid = (uint64_t)sm_count * (uint64_t)w;
   const uint64_t need = (n_runs + tiles_per_block - 1) / tiles_per_block;
@@ -698,7 +534,7 @@ void ecdna_b200_destroy(ecdna_b200_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   DevBuf* bufs[] = {&ctx->init_k, &ctx->init_c, &ctx->snap, &ctx->rates, &ctx->replay, &ctx->replay_off,
                     &ctx->abc_cdf, &ctx->arena, &ctx->counters, &ctx->scratch, &ctx->park_list, &ctx->park_rec, &ctx->ts_ring, &ctx->ts_rec, &ctx->sub_sizes, &ctx->hist_tmp,
-                    &ctx->cells, &ctx->zig};
+                    &ctx->cells, &ctx->zig, &ctx->pack_idx, &ctx->pack_out, &ctx->pack_cnt};
   for (DevBuf* b : bufs) b->release();
   for (auto& b : ctx->cols) b.release();
   cudaEventDestroy(ctx->ev_begin); cudaEventDestroy(ctx->ev_k0); cudaEventDestroy(ctx->ev_k1); cudaEventDestroy(ctx->ev_end);
@@ -729,8 +565,9 @@ int ecdna_b200_get_timing(ecdna_b200_ctx* ctx, ecdna_b200_timing_t* t) {
     CU(cudaEventSynchronize(ctx->ev_end));
     CU(cudaEventElapsedTime(&ctx->timing.total_ms, ctx->ev_begin, ctx->ev_end));
   }
-  unsigned long long tot[7];
-  CU(cudaMemcpy(tot, (char*)ctx->counters.p + 16, sizeof tot, cudaMemcpyDeviceToHost));
+  unsigned long long tot[kTotalsCount];
+  CU(cudaMemcpy(tot, (char*)ctx->counters.p + kTotalsOffset, sizeof tot, cudaMemcpyDeviceToHost));
+  ctx->timing.n_finished = tot[7];
   ctx->timing.n_slices = tot[5];
   ctx->timing.n_idle_spells = tot[6];
   ctx->timing.total_events = tot[0];
@@ -738,6 +575,8 @@ int ecdna_b200_get_timing(ecdna_b200_ctx* ctx, ecdna_b200_timing_t* t) {
   ctx->timing.alg_bytes = 4ull * tot[1] + 24ull * tot[2] + 8ull * tot[3] + 16ull * tot[0];
   ctx->timing.n_spilled = (uint32_t)tot[4];
   *t = ctx->timing;
+  if (ctx->expect_finished && tot[7] != ctx->expect_finished)
+    return fail(ctx, ECDNA_B200_ERR_INTERNAL, "internal error: " + std::to_string(tot[7]) + " of " + std::to_string(ctx->expect_finished) + " replicates finished");
   return ECDNA_B200_OK;
 }
 

@@ -1,0 +1,3 @@
+// ssa_l1.cu -- the shared-memory SSA kernel for tiles of 1 lane(s) per replicate (see ssa_kernel.cuh).
+#include "engine.cuh"
+ECDNA_DEFINE_LAUNCH_SMEM(1)

@@ -207,6 +207,9 @@ __global__ void __launch_bounds__(64) uniform_replay_kernel(const __grid_constan
     } else if (evt == ECDNA_B200_EV_DEATH_NMINUS) {
       nminus -= 1;
     } else {
+      // (the per-cell arena holds max_cells + 2 cells and the run stops at max_cells: checked before
+      //  anything is touched, so an overflow reports the pre-event state)
+      if (nplus + 1 > a.cap) { stop = ECDNA_B200_STOP_HIST_OVERFLOW; break; }
       const uint64_t idx = g.below(nplus);
       if (g.dry) { stop = ECDNA_B200_STOP_REPLAY_END; break; }
       sum_k += (uint64_t)kmax + 1u;
@@ -218,6 +221,8 @@ __global__ void __launch_bounds__(64) uniform_replay_kernel(const __grid_constan
         n_death += 1;
       } else {
         n_div += 1;
+        // (the reference panics here, proliferation.rs:63-67, with the cell already taken out at :57; the
+        //  histogram kernel and the oracle report the same state)
         if (k >= 32768u) { stop = ECDNA_B200_STOP_COPY_OVERFLOW; break; }
         const uint32_t n = 2u * k;
         uint32_t k1, k2;
@@ -234,7 +239,6 @@ __global__ void __launch_bounds__(64) uniform_replay_kernel(const __grid_constan
           }
           if (g.dry) { stop = ECDNA_B200_STOP_REPLAY_END; break; }
         }
-        if (nplus + 2 > a.cap) { stop = ECDNA_B200_STOP_HIST_OVERFLOW; break; }
         if (!uneven) {
           cells[nplus++] = (uint16_t)k1;
           cells[nplus++] = (uint16_t)k2;
@@ -279,6 +283,7 @@ __global__ void __launch_bounds__(64) uniform_replay_kernel(const __grid_constan
   atomicAdd(a.totals + 1, (unsigned long long)sum_k);
   atomicAdd(a.totals + 2, (unsigned long long)n_div);
   atomicAdd(a.totals + 3, (unsigned long long)n_death);
+  atomicAdd(a.totals + 7, 1ull);
 }
 
 }  // namespace ecdna

@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define ECDNA_B200_ABI_VERSION 2
+#define ECDNA_B200_ABI_VERSION 3
 
 /* status codes returned by every entry point */
 enum {
@@ -29,7 +29,8 @@ enum {
   ECDNA_B200_ERR_BAD_PARAMS = 1,  /* see ecdna_b200_last_error() */
   ECDNA_B200_ERR_CUDA = 2,        /* a CUDA call failed; never falls back to the CPU */
   ECDNA_B200_ERR_NO_DEVICE = 3,   /* no sm_100 device: the library refuses to run */
-  ECDNA_B200_ERR_ALLOC = 4
+  ECDNA_B200_ERR_ALLOC = 4,
+  ECDNA_B200_ERR_INTERNAL = 5     /* the library lost track of a replicate (results incomplete); a bug */
 };
 
 /* sosa reaction order, main.rs:140-145; live variants of EcDNAEvent, process.rs:20-29 */
@@ -63,7 +64,8 @@ enum {
 #define ECDNA_B200_FLAG_SPILLED 0x200u
 
 enum {
-  ECDNA_B200_RNG_PHILOX = 0,   /* native: Philox4x32-10 keyed (seed, replicate, event) */
+  ECDNA_B200_RNG_PHILOX = 0,   /* native: Philox4x32-10 keyed (seed, replicate, event), Gillespie's direct
+                                  method (one exponential + one uniform per event; stream v2) */
   ECDNA_B200_RNG_REPLAY = 1,   /* decision stream {event, dt, k, k1}: drives the histogram kernel */
   ECDNA_B200_RNG_UNIFORMS = 2  /* the reference generator's raw u64 stream: re-runs the replicate on the
                                   reference's own per-cell layout (verification mode, one thread per
@@ -127,9 +129,10 @@ typedef struct {
 
   /* engine knobs (0 = default) */
   uint32_t state_mode;  /* ECDNA_B200_STATE_* */
-  uint32_t tile_width;  /* lanes per replicate: 32 (a warp), 16, 8, 4 or 2 (2: native random source only);
+  uint32_t tile_width;  /* lanes per replicate: 32 (a warp), 16, 8, 4, 2 or 1 (2, 1: native random source only);
                            0 = the widest tile that keeps the batch within about one warp per SM scheduler
-                           (<= 592 replicates: 32, <= 1184: 16, <= 2368: 8, <= 6156: 4, more: 2) */
+                           (<= 592 replicates: 32, <= 1184: 16, <= 2368: 8, <= 6156: 4, more: 1 - a lane per
+                           replicate - when the initial copy numbers are <= 16, else 2) */
   uint32_t smem_bins;   /* histogram bins per replicate held in shared memory (rounded up to 128);
                            0 = 512, or 256 for 4- and 2-lane tiles when the initial copy numbers are <= 16 */
   uint32_t max_copies;  /* largest copy number the HBM arena holds (<= 65535) */
@@ -196,6 +199,7 @@ typedef struct {
   uint32_t slice_events;   /* slice length the launch used; 0 = it did not time-slice */
   uint64_t n_slices;       /* times a replicate made room for another one */
   uint64_t n_idle_spells;  /* times a tile of a sliced launch found nothing to run and looked again later */
+  uint64_t n_finished;     /* replicates that went through the epilogue; != n_runs is ECDNA_B200_ERR_INTERNAL */
 } ecdna_b200_timing_t;
 
 typedef struct ecdna_b200_ctx ecdna_b200_ctx;

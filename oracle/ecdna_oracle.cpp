@@ -292,6 +292,7 @@ constexpr float F_INF = std::numeric_limits<float>::infinity();
 // sosa's exprand [RECALL R2]: a normal rate draws Exp(rate); an infinite rate gives 0; anything else
 // (zero, subnormal, NaN) gives +inf WITHOUT consuming randomness.
 struct RandSource {  // rng 0
+  static constexpr bool kDirect = false;
   ChaCha8 g;
   RandSource(uint64_t seed, uint64_t run) : g(seed, run) {}
   void begin_event(uint32_t) {}
@@ -304,28 +305,50 @@ struct RandSource {  // rng 0
 };
 
 struct PhiloxSource {  // rng 1: every draw is a pure function of (seed, run, event, slot)
+  // NATIVE STREAM v2 (the specification of the CUDA kernel's native mode):
+  //   slot 0            word 0 -> the exponential waiting time of the NEXT event (Gillespie's direct
+  //                     method: dt ~ Exp(sum of propensities)); word 1 -> which reaction fires;
+  //                     words 2,3 -> high / low half of the 64-bit uniform of the cell pick
+  //   slot a*1024+1+i   all four words: bits 128i..128i+127 of segregation attempt a
+  //   slot 2^31 + j     words 0,1: the j-th redraw of the cell pick (Lemire rejection)
+  // Statistically the same process as sosa's first-reaction scheme: total rate L = sum
+  // of the lambda_i, dt ~ Exp(L), reaction i with probability lambda_i / L.
+  static constexpr bool kDirect = true;
   PhiloxKey key;
   uint32_t ev = 0;
   PhiloxSource(uint64_t seed, uint64_t run)
       : key{(uint32_t)seed, (uint32_t)(seed >> 32), (uint32_t)run, (uint32_t)(run >> 32)} {}
   void begin_event(uint32_t e) { ev = e; }
-  // slot i<4, word 0: the uniform behind reaction i's waiting time
-  float wait(int i, float lambda) {
-    if (std::isnormal(lambda)) {
-      uint32_t x[4];
-      philox_slot(key, ev, (uint32_t)i, x);
-      return neg_log_u24(x[0] >> 8) / lambda;
+  float wait(int, float) { return F_INF; }  // (first-reaction interface: unused by this source)
+  // One event of the direct method.  Propensities that are not normal numbers do not fire (sosa's
+  // exprand gives them an infinite waiting time), +inf fires at once.  Every operation is a single
+  // IEEE f32 operation in a fixed order: the kernel performs the same sequence.
+  bool next_reaction(const float lam[4], uint32_t* event, float* dt) {
+    float c[4], run = 0.f;
+    for (int i = 0; i < 4; ++i) {
+      const float lz = std::isnormal(lam[i]) ? lam[i] : ((std::isinf(lam[i]) && lam[i] > 0.f) ? F_INF : 0.f);
+      run = i == 0 ? lz : run + lz;
+      c[i] = run;
     }
-    return std::isinf(lambda) ? 0.0f : F_INF;
+    if (!(c[3] > 0.f)) return false;  // absorbing: nothing can happen
+    uint32_t x[4];
+    philox_slot(key, ev, 0u, x);
+    const float e = neg_log_u24(x[0] >> 8);
+    const float ur = (float)(x[1] >> 8) * 5.9604644775390625e-08f;  // 24 bits * 2^-24, exact
+    const bool inf = std::isinf(c[3]);
+    *dt = inf ? 0.f : e / c[3];
+    const float v = inf ? std::numeric_limits<float>::max() : ur * c[3];
+    // the number of cumulative sums <= v: v < c[3] always (ur <= 1 - 2^-24), and a reaction whose
+    // propensity is zero has the same cumulative sum as its predecessor, so it is never chosen
+    *event = (uint32_t)(v >= c[0]) + (uint32_t)(v >= c[1]) + (uint32_t)(v >= c[2]);
+    return true;
   }
-  // Lemire's unbiased bounded integer from a 64-bit uniform: first draw = word 1 of slot 0 (high)
-  // and of slot 1 (low); the rare redraw j >= 1 takes word 0 of slots 4+2j (high) and 5+2j (low)
+  // Lemire's unbiased bounded integer from a 64-bit uniform
   uint64_t pick(uint64_t n) {
     for (uint32_t j = 0;; ++j) {
-      uint32_t a[4], b[4];
-      philox_slot(key, ev, j == 0 ? 0u : 4 + 2 * j, a);
-      philox_slot(key, ev, j == 0 ? 1u : 5 + 2 * j, b);
-      const uint64_t x = j == 0 ? (((uint64_t)a[1] << 32) | b[1]) : (((uint64_t)a[0] << 32) | b[0]);
+      uint32_t a[4];
+      philox_slot(key, ev, j == 0 ? 0u : (0x80000000u + j), a);
+      const uint64_t x = j == 0 ? (((uint64_t)a[2] << 32) | a[3]) : (((uint64_t)a[0] << 32) | a[1]);
       const unsigned __int128 m = (unsigned __int128)x * n;
       const uint64_t lo = (uint64_t)m;
       if (lo >= n || j >= 13) return (uint64_t)(m >> 64);
@@ -334,14 +357,14 @@ struct PhiloxSource {  // rng 1: every draw is a pure function of (seed, run, ev
     }
   }
   // Binomial(n, 1/2) = popcount of n independent fair bits: bit b lives in slot
-  // attempt*1024 + b/64, word 2 + (b%64)/32, bit b%32.  Exact, integer only.
+  // attempt*1024 + 1 + b/128, word (b%128)/32, bit b%32.  Exact, integer only.
   uint64_t binomial_half(uint64_t n, uint32_t attempt) {
     uint64_t count = 0;
-    uint32_t slot = attempt * 1024u;
+    uint32_t slot = attempt * 1024u + 1u;
     for (uint64_t left = n; left > 0; ++slot) {
       uint32_t x[4];
       philox_slot(key, ev, slot, x);
-      for (int w = 2; w <= 3 && left > 0; ++w) {
+      for (int w = 0; w <= 3 && left > 0; ++w) {
         const uint32_t take = left >= 32 ? 32u : (uint32_t)left;
         const uint32_t mask = take == 32 ? 0xFFFFFFFFu : ((1u << take) - 1u);
         count += (uint64_t)__builtin_popcount(x[w] & mask);
@@ -506,14 +529,20 @@ int simulate(const orc_opts& o, orc_out& out, State& st, Source& src, uint64_t h
       event = r.event; dt = r.dt; rk = r.k; rk1 = r.k1;
     } else {
       src.begin_event((uint32_t)iter);
-      float best = F_INF; event = 0xffffffffu;
-      for (int i = 0; i < n_react; ++i) {
-        const float lambda = rates[i] * (float)((i & 1) ? nplus : nminus);
-        const float t = src.wait(i, lambda);
-        if (t < best) { best = t; event = (uint32_t)i; }
+      if constexpr (Source::kDirect) {  // the GPU's native stream: Gillespie's direct method
+        float lam[4];
+        for (int i = 0; i < n_react; ++i) lam[i] = rates[i] * (float)((i & 1) ? nplus : nminus);
+        if (!src.next_reaction(lam, &event, &dt)) { stop = ORC_STOP_ABSORBING; break; }
+      } else {  // sosa [RECALL R2, R3]: one waiting time per reaction, first minimum wins
+        float best = F_INF; event = 0xffffffffu;
+        for (int i = 0; i < n_react; ++i) {
+          const float lambda = rates[i] * (float)((i & 1) ? nplus : nminus);
+          const float t = src.wait(i, lambda);
+          if (t < best) { best = t; event = (uint32_t)i; }
+        }
+        if (event == 0xffffffffu) { stop = ORC_STOP_ABSORBING; break; }
+        dt = best;
       }
-      if (event == 0xffffffffu) { stop = ORC_STOP_ABSORBING; break; }
-      dt = best;
     }
 
     if (o.n_snap) snapshot_check(rec, st, time);

@@ -18,7 +18,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(HERE, "golden"))
 import make_golden  # noqa: E402
 
-GOLD = json.load(open(os.path.join(HERE, "golden", "golden_v1.json")))
+GOLD = json.load(open(os.path.join(HERE, "golden", "golden_v2.json")))
 
 
 @pytest.mark.parametrize("name", sorted(make_golden.CASES))
