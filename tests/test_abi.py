@@ -94,12 +94,14 @@ def test_launch_plan_without_a_gpu(built):
     assert built.plan(100) == (32, 1, 100, False)                  # C1: one warp per replicate
     assert built.plan(1000)[0] == 16 and built.plan(2000)[0] == 8  # C5: widest tile within one warp per scheduler
     assert built.plan(4736) == (4, 1, 4736, False)                 # exactly one block of 4-lane tiles per SM
-    lanes, w, tiles, sliced = built.plan(10_000)                   # C2: 2-lane tiles, one block per SM, sliced
-    assert (lanes, w, tiles, sliced) == (2, 1, 9472, True)
+    lanes, w, tiles, sliced = built.plan(10_000)                   # C2: a lane per replicate, 157 blocks of two warps
+    assert (lanes, w, tiles, sliced) == (1, 3, 10_048, False)
+    assert built.plan(10_000, tile_width=2) == (2, 1, 9472, True)  # 2-lane tiles: one block per SM, sliced
     assert built.plan(9472, tile_width=2) == (2, 1, 9472, False)   # an exact fit needs no slicing
     assert built.plan(10_000, tile_width=4) == (4, 2, 9472, True)
     assert built.plan(10_000, tile_width=4, slice_events=0xFFFFFFFF) == (4, 5, 10_016, False)
-    assert built.plan(1_000_000) == (2, 3, 28_416, False)          # C4: many waves, the queue balances them
-    assert built.plan(16_384) == (2, 2, 16_384, False)
-    with pytest.raises(built.EcdnaB200Error):
+    assert built.plan(1_000_000) == (1, 3, 28_416, False)          # C4: many waves, the queue balances them
+    assert built.plan(1_000_000, tile_width=2) == (2, 3, 28_416, False)
+    assert built.plan(16_384) == (1, 3, 16_384, False)
+    with pytest.raises(Exception):
         built.plan(100, tile_width=3)
