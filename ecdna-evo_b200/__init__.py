@@ -17,7 +17,8 @@ import numpy as np
 
 from .build import LIB_PATH, build  # noqa: F401
 from .shard import gather_accepted, rank_range  # noqa: F401
-from .abc import ABC_FIELDS, abc_rows, write_abc_csv  # noqa: F401
+from .abc import (ABC_FIELDS, REC_HEADER, abc_rows, decode_records, merge_gathered, record_words,  # noqa: F401
+                  write_abc_csv)
 
 ABI_VERSION = 3
 EV_BIRTH_NMINUS, EV_BIRTH_NPLUS, EV_DEATH_NMINUS, EV_DEATH_NPLUS = 0, 1, 2, 3
@@ -101,8 +102,11 @@ class TimingT(C.Structure):
 EXPORTED_SYMBOLS = [
     "ecdna_b200_create", "ecdna_b200_destroy", "ecdna_b200_last_error", "ecdna_b200_abi_version", "ecdna_b200_run",
     "ecdna_b200_run_device", "ecdna_b200_get_timing", "ecdna_b200_abc_draw_priors", "ecdna_b200_compact_accepted",
-    "ecdna_b200_plan",
+    "ecdna_b200_plan", "ecdna_b200_abc_draw_priors_device", "ecdna_b200_abc_pack", "ecdna_b200_abc_allgather",
+    "ecdna_b200_comm_unique_id", "ecdna_b200_comm_init", "ecdna_b200_comm_init_all", "ecdna_b200_comm_release",
 ]
+ERR_INTERNAL, ERR_COMM = 5, 6
+COMM_ID_BYTES = 128
 
 _lib = None
 
@@ -143,8 +147,30 @@ def lib():
                                                  C.c_void_p]
         L.ecdna_b200_compact_accepted.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p,
                                                   C.POINTER(C.c_uint32), C.c_void_p]
+        L.ecdna_b200_abc_draw_priors_device.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_float,
+                                                        C.POINTER(C.c_float), C.POINTER(C.c_float),
+                                                        C.POINTER(C.c_float), C.c_void_p, C.c_void_p]
+        L.ecdna_b200_abc_pack.argtypes = [C.c_void_p, C.POINTER(ResultsT), C.c_void_p, C.POINTER(C.c_float), C.c_uint64,
+                                          C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p,
+                                          C.c_void_p]
+        L.ecdna_b200_abc_allgather.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p,
+                                               C.c_void_p, C.c_void_p]
+        L.ecdna_b200_comm_unique_id.argtypes = [C.c_void_p]
+        L.ecdna_b200_comm_init.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+        L.ecdna_b200_comm_init_all.argtypes = [C.POINTER(C.c_void_p), C.c_int]
+        L.ecdna_b200_comm_release.argtypes = [C.c_void_p]
+        L.ecdna_b200_comm_release.restype = None
         _lib = L
     return _lib
+
+
+def comm_unique_id():
+    """ecdna_b200_comm_unique_id: 128 bytes rank 0 hands to every rank (ncclUniqueId)."""
+    buf = (C.c_uint8 * COMM_ID_BYTES)()
+    rc = lib().ecdna_b200_comm_unique_id(buf)
+    if rc != 0:
+        raise EcdnaB200Error(f"ecdna_b200_comm_unique_id: status {rc} (6 = NCCL not available)")
+    return bytes(buf)
 
 
 class EcdnaB200Error(RuntimeError):
@@ -348,6 +374,35 @@ class Context:
         self._check(lib().ecdna_b200_abc_draw_priors(self._h, seed, idx_begin, n_runs, b0, r1, r2, r3,
                                                      out.ctypes.data))
         return out
+
+    def abc_draw_priors_device(self, seed, idx_begin, n_runs, rates_dev_ptr, b0=1.0, b1_range=(1.0, 2.0),
+                               d0_range=(0.0, 0.5), d1_range=(0.0, 0.5), stream=None):
+        r1, r2, r3 = (C.c_float * 2)(*b1_range), (C.c_float * 2)(*d0_range), (C.c_float * 2)(*d1_range)
+        self._check(lib().ecdna_b200_abc_draw_priors_device(self._h, seed, idx_begin, n_runs, b0, r1, r2, r3,
+                                                            C.c_void_p(rates_dev_ptr),
+                                                            C.c_void_p(stream) if stream else None))
+
+    def abc_pack(self, results_struct, rates_dev_ptr, base_rates, idx_begin, n_runs, hist_stride, rec_bins, capacity,
+                 records_dev_ptr, count_dev_ptr, stream=None):
+        """ecdna_b200_abc_pack: accepted draws -> fixed-stride records on the device, in index order."""
+        base = (C.c_float * 4)(*base_rates)
+        self._check(lib().ecdna_b200_abc_pack(self._h, C.byref(results_struct),
+                                              C.c_void_p(rates_dev_ptr) if rates_dev_ptr else None, base, idx_begin,
+                                              n_runs, hist_stride, rec_bins, capacity, C.c_void_p(records_dev_ptr),
+                                              C.c_void_p(count_dev_ptr), C.c_void_p(stream) if stream else None))
+
+    def comm_init(self, unique_id, rank, world):
+        """ecdna_b200_comm_init: join the NCCL communicator of the GPUs that share a batch."""
+        buf = (C.c_uint8 * COMM_ID_BYTES).from_buffer_copy(unique_id)
+        self._check(lib().ecdna_b200_comm_init(self._h, buf, rank, world))
+
+    def abc_allgather(self, records_dev_ptr, count_dev_ptr, rec_bins, capacity, all_records_dev_ptr, all_counts_dev_ptr,
+                      stream=None):
+        """ecdna_b200_abc_allgather: counts + record blocks of every rank, two ncclAllGather in one group."""
+        self._check(lib().ecdna_b200_abc_allgather(self._h, C.c_void_p(records_dev_ptr), C.c_void_p(count_dev_ptr),
+                                                   rec_bins, capacity, C.c_void_p(all_records_dev_ptr),
+                                                   C.c_void_p(all_counts_dev_ptr),
+                                                   C.c_void_p(stream) if stream else None))
 
     def compact_accepted(self, accept_dev_ptr, n_runs, out_idx_dev_ptr, stream=None):
         n = C.c_uint32(0)

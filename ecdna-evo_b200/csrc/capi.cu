@@ -532,6 +532,7 @@ void ecdna_b200_destroy(ecdna_b200_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  ecdna_b200_comm_release(ctx);
   DevBuf* bufs[] = {&ctx->init_k, &ctx->init_c, &ctx->snap, &ctx->rates, &ctx->replay, &ctx->replay_off,
                     &ctx->abc_cdf, &ctx->arena, &ctx->counters, &ctx->scratch, &ctx->park_list, &ctx->park_rec, &ctx->ts_ring, &ctx->ts_rec, &ctx->sub_sizes, &ctx->hist_tmp,
                     &ctx->cells, &ctx->zig, &ctx->pack_idx, &ctx->pack_out, &ctx->pack_cnt};
@@ -593,6 +594,19 @@ int ecdna_b200_abc_draw_priors(ecdna_b200_ctx* ctx, uint64_t seed, uint64_t idx_
   CU(cudaGetLastError());
   CU(cudaMemcpyAsync(rates_out, ctx->rates.p, n_runs * 16, cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
+  return ECDNA_B200_OK;
+}
+
+int ecdna_b200_abc_draw_priors_device(ecdna_b200_ctx* ctx, uint64_t seed, uint64_t idx_begin, uint64_t n_runs, float b0,
+                                      const float b1_range[2], const float d0_range[2], const float d1_range[2],
+                                      float* rates_dev, void* cuda_stream) {
+  if (!ctx || !rates_dev || n_runs == 0 || n_runs >= (1ull << 32)) return fail(ctx, ECDNA_B200_ERR_BAD_PARAMS, "bad prior request");
+  CU(cudaSetDevice(ctx->device));
+  const uint32_t n = (uint32_t)n_runs;
+  cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
+  prior_kernel<<<(n + 255) / 256, 256, 0, st>>>((uint32_t)seed, (uint32_t)(seed >> 32), idx_begin, n, b0, b1_range[0],
+                                                b1_range[1], d0_range[0], d0_range[1], d1_range[0], d1_range[1], rates_dev);
+  CU(cudaGetLastError());
   return ECDNA_B200_OK;
 }
 

@@ -46,8 +46,11 @@ constexpr size_t kRingCtrOffset = 96;  // 4 x u32 (SsaArgs::ts_ctr)
 
 }  // namespace ecdna
 
+struct ecdna_b200_comm;  // abc_gather.cu
+
 struct ecdna_b200_ctx {
   int device = 0;
+  ecdna_b200_comm* comm = nullptr;
   int sm_count = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev_begin = nullptr, ev_k0 = nullptr, ev_k1 = nullptr, ev_end = nullptr;

@@ -30,7 +30,8 @@ enum {
   ECDNA_B200_ERR_CUDA = 2,        /* a CUDA call failed; never falls back to the CPU */
   ECDNA_B200_ERR_NO_DEVICE = 3,   /* no sm_100 device: the library refuses to run */
   ECDNA_B200_ERR_ALLOC = 4,
-  ECDNA_B200_ERR_INTERNAL = 5     /* the library lost track of a replicate (results incomplete); a bug */
+  ECDNA_B200_ERR_INTERNAL = 5,    /* the library lost track of a replicate (results incomplete); a bug */
+  ECDNA_B200_ERR_COMM = 6         /* NCCL is missing or a collective failed */
 };
 
 /* sosa reaction order, main.rs:140-145; live variants of EcDNAEvent, process.rs:20-29 */
@@ -239,10 +240,49 @@ int ecdna_b200_abc_draw_priors(ecdna_b200_ctx* ctx, uint64_t seed, uint64_t idx_
                                const float b1_range[2], const float d0_range[2], const float d1_range[2],
                                float* rates_out /* [n_runs][4], host */);
 
+/* Same draws, left on the device: `rates_dev` is a device buffer [n_runs][4]; enqueued on `cuda_stream`
+   (NULL = the context's stream) without a synchronisation. */
+int ecdna_b200_abc_draw_priors_device(ecdna_b200_ctx* ctx, uint64_t seed, uint64_t idx_begin, uint64_t n_runs, float b0,
+                                      const float b1_range[2], const float d0_range[2], const float d1_range[2],
+                                      float* rates_dev, void* cuda_stream);
+
 /* Compacts the accepted runs of the last ecdna_b200_run_device call: writes their indices
    (relative to idx_begin) to `accepted_idx` (device, [n_runs]) and the count to *n_accepted (host). */
 int ecdna_b200_compact_accepted(ecdna_b200_ctx* ctx, const uint8_t* accept_dev, uint64_t n_runs,
                                 uint32_t* accepted_idx_dev, uint32_t* n_accepted, void* cuda_stream);
+
+/* ---- the one exchange step of the path: all-gather of the accepted ABC draws (abc.md:57-78) ----
+   A record is ECDNA_B200_ABC_REC_HEADER + rec_bins 32-bit words:
+     [0..1] replicate index (lo, hi)   [2..5] b0, b1, d0, d1 (f32 bits)   [6..9] the four distances (f32 bits)
+     [10] mean  [11] frequency  [12] entropy (f32 bits)   [13] cells   [14] kmax   [15] stop_reason
+     [16..] the final distribution, rec_bins bins ([16] = cells without ecDNA)                               */
+#define ECDNA_B200_ABC_REC_HEADER 16u
+#define ECDNA_B200_COMM_ID_BYTES 128
+
+/* Packs the accepted draws (abc_accept != 0) of a batch whose result columns live on the device into
+   records, in index order, on `cuda_stream`; *count_dev (device) receives the number of accepted draws,
+   which may exceed `capacity` (then only the first `capacity` records were written).  rates_dev: the
+   per-run rates [n_runs][4] on the device, or NULL (then base_rates[4] goes into every record). */
+int ecdna_b200_abc_pack(ecdna_b200_ctx* ctx, const ecdna_b200_results_t* results_dev, const float* rates_dev,
+                        const float base_rates[4], uint64_t idx_begin, uint64_t n_runs, uint32_t hist_stride,
+                        uint32_t rec_bins, uint32_t capacity, uint32_t* records_dev, uint32_t* count_dev,
+                        void* cuda_stream);
+
+/* Communicator over the GPUs that share a batch: NCCL (NVLink 5 / NVSwitch inside one box), loaded with
+   dlopen("libnccl.so.2") on first use.  One process per GPU: rank 0 calls _unique_id, the caller gets
+   the 128 bytes to every rank (MPI, the launcher's rendezvous, a file ...) and every rank calls _comm_init.
+   One process, several GPUs: _comm_init_all on the contexts.  ecdna_b200_destroy releases it. */
+int ecdna_b200_comm_unique_id(uint8_t id[ECDNA_B200_COMM_ID_BYTES]);
+int ecdna_b200_comm_init(ecdna_b200_ctx* ctx, const uint8_t id[ECDNA_B200_COMM_ID_BYTES], int rank, int world);
+int ecdna_b200_comm_init_all(ecdna_b200_ctx* const* ctxs, int n);
+void ecdna_b200_comm_release(ecdna_b200_ctx* ctx);
+
+/* All-gather of the packed records: every rank contributes its count and a block of `capacity` records;
+   all_counts_dev [world] and all_records_dev [world][capacity][record] (device) receive them in rank order.
+   Two ncclAllGather calls in one group on `cuda_stream`; no host synchronisation. */
+int ecdna_b200_abc_allgather(ecdna_b200_ctx* ctx, const uint32_t* records_dev, const uint32_t* count_dev,
+                             uint32_t rec_bins, uint32_t capacity, uint32_t* all_records_dev,
+                             uint32_t* all_counts_dev, void* cuda_stream);
 
 #ifdef __cplusplus
 }

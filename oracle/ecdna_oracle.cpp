@@ -326,7 +326,7 @@ struct PhiloxSource {  // rng 1: every draw is a pure function of (seed, run, ev
   bool next_reaction(const float lam[4], uint32_t* event, float* dt) {
     float c[4], run = 0.f;
     for (int i = 0; i < 4; ++i) {
-      const float lz = std::isnormal(lam[i]) ? lam[i] : ((std::isinf(lam[i]) && lam[i] > 0.f) ? F_INF : 0.f);
+      const float lz = (std::isnormal(lam[i]) && lam[i] > 0.f) ? lam[i] : ((std::isinf(lam[i]) && lam[i] > 0.f) ? F_INF : 0.f);
       run = i == 0 ? lz : run + lz;
       c[i] = run;
     }
@@ -718,6 +718,58 @@ uint64_t orc_run_batch(const orc_opts* o, uint64_t idx_begin, uint64_t n_runs, i
       if (nminus) nminus[i] = out.nminus;
       if (nplus) nplus[i] = out.nplus;
       if (time) time[i] = out.time;
+      if (n_events) n_events[i] = out.n_events;
+      if (stop) stop[i] = out.stop_reason;
+      local += out.n_events;
+    }
+    total += local;
+  };
+  std::vector<std::thread> th;
+  for (int t = 1; t < n_threads; ++t) th.emplace_back(worker);
+  worker();
+  for (auto& t : th) t.join();
+  return total.load();
+}
+
+// ABC over a batch of prior draws (abc.md:38-55): every draw is one replicate with its own rates plus the
+// four distances of its final distribution to the target (KS on the ecDNA distribution, relative mean,
+// relative entropy, relative frequency) and the accept flag; what the kernel's fused epilogue computes.
+uint64_t orc_abc_batch(const orc_opts* o, uint64_t idx_begin, uint64_t n_runs, int n_threads, const float* rates_per_run,
+                       const uint64_t* target, uint32_t target_len, const float thresholds[4], uint32_t hist_cap,
+                       float* distances /* [n][4] */, uint8_t* accept /* [n] */, uint64_t* n_events /* [n] or NULL */,
+                       uint32_t* stop /* [n] or NULL */) {
+  if (n_threads <= 0) n_threads = (int)std::thread::hardware_concurrency();
+  if (n_threads <= 0) n_threads = 1;
+  float tm, tf, te, tv;
+  stats_from_dense(target, target_len, &tm, &tf, &te, &tv);
+  std::atomic<uint64_t> next{0}, total{0};
+  auto worker = [&]() {
+    uint64_t local = 0;
+    std::vector<uint64_t> hist(hist_cap);
+    for (;;) {
+      const uint64_t i = next.fetch_add(1);
+      if (i >= n_runs) break;
+      orc_opts oo = *o;
+      oo.run_idx = idx_begin + i;
+      if (rates_per_run) { oo.b0 = rates_per_run[4 * i]; oo.b1 = rates_per_run[4 * i + 1]; oo.d0 = rates_per_run[4 * i + 2]; oo.d1 = rates_per_run[4 * i + 3]; }
+      orc_out out;
+      std::memset(&out, 0, sizeof out);
+      out.hist_cap = hist_cap;
+      out.hist = hist.data();
+      orc_run(&oo, &out);
+      float m, f, e, v;
+      stats_from_dense(hist.data(), hist_cap, &m, &f, &e, &v);
+      float d[4];
+      d[0] = orc_ks_distance(hist.data(), hist_cap, target, target_len);
+      d[1] = std::fabs(m - tm) / tm;
+      d[2] = std::fabs(e - te) / te;
+      d[3] = std::fabs(f - tf) / tf;
+      bool ok = true;
+      for (int j = 0; j < 4; ++j) {
+        if (distances) distances[4 * i + j] = d[j];
+        if (thresholds[j] >= 0.f && !(d[j] <= thresholds[j])) ok = false;
+      }
+      if (accept) accept[i] = ok ? 1 : 0;
       if (n_events) n_events[i] = out.n_events;
       if (stop) stop[i] = out.stop_reason;
       local += out.n_events;

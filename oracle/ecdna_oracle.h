@@ -28,8 +28,10 @@
  *   rng 0 "rand"    ChaCha8(seed).set_stream(idx) (main.rs:57-58) with rand-0.8
  *                   conversions, ziggurat Exp1, BINV/BTPE binomial [RECALL]
  *   rng 1 "philox"  Philox4x32-10, key=(seed), counter=(event, slot, run): the
- *                   GPU's native stream (slot layout in ecdna_oracle.cpp PhiloxSource); exponentials by a deterministic f32 log,
- *                   Binomial(2k,1/2) as the popcount of 2k random bits (exact)
+ *                   GPU's native stream v2 (slot layout in ecdna_oracle.cpp PhiloxSource): Gillespie's
+ *                   direct method - one exponential waiting time with the summed propensity (a deterministic
+ *                   f32 log) and one uniform that picks the reaction - and Binomial(2k,1/2) as the
+ *                   popcount of 2k random bits (exact)
  *   rng 2 "replay"  consumes a decision stream {event, dt, k, k1} (histogram state
  *                   only); the stream is what either state emits as trace_out.
  */
@@ -121,6 +123,14 @@ uint64_t orc_run_batch(const orc_opts* o, uint64_t idx_begin, uint64_t n_runs, i
                        uint64_t* nminus, uint64_t* nplus, float* time, uint64_t* n_events,
                        uint32_t* stop, uint64_t* hist /* [n_runs][hist_cap] or NULL */, uint32_t hist_cap,
                        const float* rates_per_run /* [n_runs][4] or NULL */);
+
+/* ABC over a batch of prior draws (abc.md:38-55): per draw one replicate with rates_per_run[i] and the four
+   distances of its final distribution to `target` (dense, [0] = cells without ecDNA): KS, relative mean,
+   relative entropy, relative frequency [RECALL R8]; accept = every distance <= its threshold (a negative
+   threshold is ignored).  Returns total events. */
+uint64_t orc_abc_batch(const orc_opts* o, uint64_t idx_begin, uint64_t n_runs, int n_threads, const float* rates_per_run,
+                       const uint64_t* target, uint32_t target_len, const float thresholds[4], uint32_t hist_cap,
+                       float* distances, uint8_t* accept, uint64_t* n_events, uint32_t* stop);
 
 /* summary statistics over a dense histogram (hist[0] = cells without ecDNA) [RECALL R8] */
 void orc_stats(const uint64_t* hist, uint32_t cap, float* mean, float* frequency, float* entropy, float* variance);

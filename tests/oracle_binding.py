@@ -56,27 +56,59 @@ class Out(C.Structure):
     ]
 
 
+_SO_FAST = os.path.join(_ORACLE_DIR, "libecdna_oracle_fast.so")
+
+
 def build(force=False):
     src = [os.path.join(_ORACLE_DIR, f) for f in ("ecdna_oracle.cpp", "ecdna_oracle.h", "Makefile")]
-    stale = (not os.path.exists(_SO)) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in src)
+    stale = any((not os.path.exists(so)) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in src)
+                for so in (_SO, _SO_FAST))
     if force or stale:
         subprocess.run(["make", "-C", _ORACLE_DIR, "-B" if force else "-s"], check=True, capture_output=True)
     return _SO
 
 
 _lib = None
+_use_fast = False
+
+
+def _host_signature():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("flags"):
+                import hashlib
+                return hashlib.sha256(line.encode()).hexdigest()
+    except OSError:
+        pass
+    return "unknown"
+
+
+def use_fast_build():
+    """bench.py's CPU legs time the -O3 -march=native build of the same source; tests never call this.
+    -march=native code must be compiled on the host that runs it: rebuilt when the CPU's flags differ."""
+    global _lib, _use_fast
+    if not _use_fast:
+        stamp = _SO_FAST + ".host"
+        sig = _host_signature()
+        if not os.path.exists(_SO_FAST) or not os.path.exists(stamp) or open(stamp).read().strip() != sig:
+            subprocess.run(["make", "-C", _ORACLE_DIR, "-B", "libecdna_oracle_fast.so"], check=True, capture_output=True)
+            open(stamp, "w").write(sig)
+        _use_fast, _lib = True, None
 
 
 def lib():
     global _lib
     if _lib is None:
         build()
-        L = C.CDLL(_SO)
+        L = C.CDLL(_SO_FAST if _use_fast else _SO)
         L.orc_run.argtypes = [C.POINTER(Opts), C.POINTER(Out)]
         L.orc_run.restype = C.c_int
         L.orc_run_batch.argtypes = [C.POINTER(Opts), C.c_uint64, C.c_uint64, C.c_int] + [C.c_void_p] * 6 + [
             C.c_uint32, C.c_void_p]
         L.orc_run_batch.restype = C.c_uint64
+        L.orc_abc_batch.argtypes = [C.POINTER(Opts), C.c_uint64, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p, C.c_uint32,
+                                    C.POINTER(C.c_float), C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_abc_batch.restype = C.c_uint64
         L.orc_stats.argtypes = [C.c_void_p, C.c_uint32] + [C.POINTER(C.c_float)] * 4
         L.orc_ks_distance.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32]
         L.orc_ks_distance.restype = C.c_float
@@ -191,6 +223,21 @@ def run_batch(opts, idx_begin, n_runs, n_threads=0, hist_cap=0, rates=None):
     r.total_events = lib().orc_run_batch(C.byref(opts), idx_begin, n_runs, n_threads, _ptr(r.nminus), _ptr(r.nplus),
                                          _ptr(r.time), _ptr(r.n_events), _ptr(r.stop), _ptr(r.hist), hist_cap,
                                          _ptr(rates_c))
+    return r
+
+
+def abc_batch(opts, idx_begin, n_runs, rates, target, thresholds, n_threads=0, hist_cap=512):
+    """orc_abc_batch: prior draws -> replicates -> the four ABC distances and the accept flag per draw."""
+    r = Result()
+    r.distance = np.zeros((n_runs, 4), dtype=np.float32)
+    r.accept = np.zeros(n_runs, dtype=np.uint8)
+    r.n_events = np.zeros(n_runs, dtype=np.uint64)
+    r.stop = np.zeros(n_runs, dtype=np.uint32)
+    rates_c = np.ascontiguousarray(rates, dtype=np.float32)
+    tgt = np.ascontiguousarray(target, dtype=np.uint64)
+    thr = (C.c_float * 4)(*thresholds)
+    r.total_events = lib().orc_abc_batch(C.byref(opts), idx_begin, n_runs, n_threads, _ptr(rates_c), _ptr(tgt), len(tgt), thr,
+                                         hist_cap, _ptr(r.distance), _ptr(r.accept), _ptr(r.n_events), _ptr(r.stop))
     return r
 
 
