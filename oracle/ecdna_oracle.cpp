@@ -122,12 +122,21 @@ struct ChaCha8 {
   int index = 64;  // 4 blocks buffered, refilled when exhausted
   uint64_t* rec = nullptr;  // optional export of every u64 handed out (what a recording RngCore sees)
   uint64_t rec_cap = 0, rec_len = 0;
+  // optional EXTERNAL stream: the u64 log of a real reference run replaces the
+  // generator, so that every conversion downstream of it is checked against the reference's own output
+  const uint64_t* ext = nullptr;
+  uint64_t ext_len = 0, ext_pos = 0;
+  bool dry = false;
   ChaCha8(uint64_t seed, uint64_t stream_id) : stream(stream_id) { seed_from_u64(seed, key); }
   void refill() {
     for (int b = 0; b < 4; ++b) chacha_block(key, counter + b, stream, 8, buf + 16 * b);
     counter += 4;
   }
   uint64_t next_u64() {
+    if (ext) {
+      if (ext_pos >= ext_len) { dry = true; return 0; }  // (0 ends every rejection loop downstream)
+      return ext[ext_pos++];
+    }
     const uint64_t v = raw_u64();
     if (rec) {
       if (rec_len < rec_cap) rec[rec_len] = v;
@@ -295,6 +304,7 @@ struct RandSource {  // rng 0
   static constexpr bool kDirect = false;
   ChaCha8 g;
   RandSource(uint64_t seed, uint64_t run) : g(seed, run) {}
+  bool dry() const { return g.dry; }
   void begin_event(uint32_t) {}
   float wait(int, float lambda) {
     if (std::isnormal(lambda)) return (float)exp1_f64(g) * (1.0f / lambda);
@@ -314,6 +324,7 @@ struct PhiloxSource {  // rng 1: every draw is a pure function of (seed, run, ev
   // Statistically the same process as sosa's first-reaction scheme: total rate L = sum
   // of the lambda_i, dt ~ Exp(L), reaction i with probability lambda_i / L.
   static constexpr bool kDirect = true;
+  bool dry() const { return false; }
   PhiloxKey key;
   uint32_t ev = 0;
   PhiloxSource(uint64_t seed, uint64_t run)
@@ -540,6 +551,7 @@ int simulate(const orc_opts& o, orc_out& out, State& st, Source& src, uint64_t h
           const float t = src.wait(i, lambda);
           if (t < best) { best = t; event = (uint32_t)i; }
         }
+        if (src.dry()) { stop = ORC_STOP_REPLAY_END; break; }
         if (event == 0xffffffffu) { stop = ORC_STOP_ABSORBING; break; }
         dt = best;
       }
@@ -556,16 +568,21 @@ int simulate(const orc_opts& o, orc_out& out, State& st, Source& src, uint64_t h
       st.nminus -= 1;  // proliferation.rs:135-139
     } else {
       if (REPLAY && nplus == 0) { stop = ORC_STOP_REPLAY_BAD; break; }
-      sum_k += (uint64_t)kmax + 1;
       // pick a uniformly random ecDNA+ cell and take it out (proliferation.rs:57 / 126-133)
+      uint64_t pidx = 0;
+      if (!REPLAY) {
+        pidx = src.pick(nplus);
+        if (src.dry()) { stop = ORC_STOP_REPLAY_END; break; }
+      }
+      sum_k += (uint64_t)kmax + 1;
       if constexpr (std::is_same<State, VectorState>::value) {
-        k = st.remove_at(src.pick(nplus));
+        k = st.remove_at(pidx);
       } else {
         if (REPLAY) {
           k = rk;
           if (k == 0 || k > st.kmax || st.h[k] == 0) { stop = ORC_STOP_REPLAY_BAD; break; }
         } else {
-          k = st.class_at(src.pick(nplus));
+          k = st.class_at(pidx);
         }
         st.h[k] -= 1; st.np -= 1;
       }
@@ -591,9 +608,10 @@ int simulate(const orc_opts& o, orc_out& out, State& st, Source& src, uint64_t h
             k1 = (uint32_t)src.binomial_half(n, attempt);
             k2 = n - k1;
             uneven = (k1 == 0 || k2 == 0);
-            if (!(uneven && o.segregation == ORC_SEG_BINOMIAL_NO_UNEVEN)) break;
+            if (src.dry() || !(uneven && o.segregation == ORC_SEG_BINOMIAL_NO_UNEVEN)) break;
             ++attempt;
           }
+          if (src.dry()) { stop = ORC_STOP_REPLAY_END; break; }
         }
         auto add = [&](uint32_t kk) {
           if constexpr (std::is_same<State, VectorState>::value) st.push(kk);
@@ -679,8 +697,9 @@ int orc_run(const orc_opts* o, orc_out* out) {
     if (o->rng == 0) {
       RandSource s(o->seed, o->run_idx);
       s.g.rec = out->u64_out; s.g.rec_cap = out->u64_cap;
+      if (o->u64_in) { s.g.ext = o->u64_in; s.g.ext_len = o->u64_in_len; }
       const int rc = simulate<VectorState, RandSource, false>(*o, *out, st, s, h0);
-      out->u64_len = s.g.rec_len;
+      out->u64_len = o->u64_in ? s.g.ext_pos : s.g.rec_len;
       return rc;
     }
     PhiloxSource s(o->seed, o->run_idx);

@@ -87,6 +87,11 @@ typedef struct {
   float dyn_dt;
   const orc_replay_event* replay_in;
   uint64_t replay_len;
+  /* vector state + rng "rand": when set, these u64 (the log of a recording RngCore around the REAL
+     reference's ChaCha8Rng) replace the generator; u64_len of orc_out then
+     reports how many were consumed and a stream that ends early stops with ORC_STOP_REPLAY_END */
+  const uint64_t* u64_in;
+  uint64_t u64_in_len;
 } orc_opts;
 
 typedef struct {

@@ -36,6 +36,7 @@ class Opts(C.Structure):
         ("n_snap", C.c_uint32), ("snap_cells", C.c_void_p),
         ("dyn_points", C.c_uint32), ("dyn_dt", C.c_float),
         ("replay_in", C.c_void_p), ("replay_len", C.c_uint64),
+        ("u64_in", C.c_void_p), ("u64_in_len", C.c_uint64),
     ]
 
 
@@ -149,7 +150,7 @@ class Result:
 
 def make_opts(b0=1.0, b1=1.0, d0=0.0, d1=0.0, segregation=SEG_BINOMIAL, state=STATE_HIST, rng=RNG_PHILOX,
               max_cells=1000, max_iter=1_000_000_000, max_time=None, seed=26, run_idx=260, initial=None,
-              snapshots=None, dyn_points=0, dyn_dt=0.1, replay=None, bd_count_mode=0):
+              snapshots=None, dyn_points=0, dyn_dt=0.1, replay=None, bd_count_mode=0, u64_in=None):
     """Mirror of SimulationOptions (main.rs:28-44) + Options (clap_app.rs:204-209)."""
     if max_time is None:
         max_time = float(int(np.log2(np.float32(max_cells)) + np.float32(4.0)))  # clap_app.rs:151
@@ -170,6 +171,9 @@ def make_opts(b0=1.0, b1=1.0, d0=0.0, d1=0.0, segregation=SEG_BINOMIAL, state=ST
     o.dyn_points, o.dyn_dt = dyn_points, dyn_dt
     if keep["replay"] is not None:
         o.replay_in, o.replay_len = _ptr(keep["replay"]), len(keep["replay"])
+    if u64_in is not None:
+        keep["u64_in"] = np.ascontiguousarray(u64_in, dtype=np.uint64)
+        o.u64_in, o.u64_in_len = _ptr(keep["u64_in"]), len(keep["u64_in"])
     o._keep = keep
     return o
 
