@@ -103,7 +103,9 @@ EXPORTED_SYMBOLS = [
     "ecdna_b200_create", "ecdna_b200_destroy", "ecdna_b200_last_error", "ecdna_b200_abi_version", "ecdna_b200_run",
     "ecdna_b200_run_device", "ecdna_b200_get_timing", "ecdna_b200_abc_draw_priors", "ecdna_b200_compact_accepted",
     "ecdna_b200_plan", "ecdna_b200_abc_draw_priors_device", "ecdna_b200_abc_pack", "ecdna_b200_abc_allgather",
-    "ecdna_b200_comm_unique_id", "ecdna_b200_comm_init", "ecdna_b200_comm_init_all", "ecdna_b200_comm_release",
+    "ecdna_b200_comm_unique_id", "ecdna_b200_comm_init", "ecdna_b200_comm_release",
+    "ecdna_b200_multi_create", "ecdna_b200_multi_destroy", "ecdna_b200_multi_device_count",
+    "ecdna_b200_multi_last_error", "ecdna_b200_multi_run", "ecdna_b200_multi_get_timing",
 ]
 ERR_INTERNAL, ERR_COMM = 5, 6
 COMM_ID_BYTES = 128
@@ -157,7 +159,14 @@ def lib():
                                                C.c_void_p, C.c_void_p]
         L.ecdna_b200_comm_unique_id.argtypes = [C.c_void_p]
         L.ecdna_b200_comm_init.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
-        L.ecdna_b200_comm_init_all.argtypes = [C.POINTER(C.c_void_p), C.c_int]
+        L.ecdna_b200_multi_create.argtypes = [C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_void_p)]
+        L.ecdna_b200_multi_destroy.argtypes = [C.c_void_p]
+        L.ecdna_b200_multi_destroy.restype = None
+        L.ecdna_b200_multi_device_count.argtypes = [C.c_void_p]
+        L.ecdna_b200_multi_last_error.argtypes = [C.c_void_p]
+        L.ecdna_b200_multi_last_error.restype = C.c_char_p
+        L.ecdna_b200_multi_run.argtypes = [C.c_void_p, C.POINTER(ParamsT), C.c_uint64, C.c_uint64, C.POINTER(ResultsT)]
+        L.ecdna_b200_multi_get_timing.argtypes = [C.c_void_p, C.POINTER(TimingT)]
         L.ecdna_b200_comm_release.argtypes = [C.c_void_p]
         L.ecdna_b200_comm_release.restype = None
         _lib = L
@@ -410,6 +419,43 @@ class Context:
                                                       C.c_void_p(out_idx_dev_ptr), C.byref(n),
                                                       C.c_void_p(stream) if stream else None))
         return n.value
+
+
+class MultiContext(Context):
+    """Several GPUs of one box from one process (ecdna_b200_multi): the index range is cut into contiguous
+    blocks, one per GPU; outputs are identical to a one-GPU run of the same range."""
+
+    def __init__(self, devices=None):
+        self._h = C.c_void_p()
+        arr = (C.c_int * len(devices))(*devices) if devices else None
+        rc = lib().ecdna_b200_multi_create(arr, len(devices) if devices else 0, C.byref(self._h))
+        if rc != 0:
+            raise EcdnaB200Error(f"ecdna_b200_multi_create failed with status {rc} (3 = no sm_100 device)")
+        self.n_devices = lib().ecdna_b200_multi_device_count(self._h)
+
+    def close(self):
+        if self._h:
+            lib().ecdna_b200_multi_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def _check(self, rc):
+        if rc != 0:
+            raise EcdnaB200Error(f"status {rc}: {lib().ecdna_b200_multi_last_error(self._h).decode()}")
+
+    def run(self, opts, n_runs=None, idx_begin=None, want=("stop_reason", "nminus", "nplus", "time", "n_events",
+                                                           "kmax", "hist"), **kw):
+        n_runs = opts.runs if n_runs is None else n_runs
+        idx_begin = opts.idx_begin if idx_begin is None else idx_begin
+        p = self.make_params(opts, n_runs, **kw)
+        res = Results(n_runs, p.n_snapshots, p.dyn_points, p.hist_stride or 512, want, p.n_subsamples)
+        self._check(lib().ecdna_b200_multi_run(self._h, C.byref(p), idx_begin, n_runs, C.byref(res.struct)))
+        res.timing = self.timing()
+        return res
+
+    def timing(self):
+        t = TimingT()
+        self._check(lib().ecdna_b200_multi_get_timing(self._h, C.byref(t)))
+        return t
 
 
 def _addr(a):

@@ -23,7 +23,6 @@ struct NcclApi {
   void* handle = nullptr;
   decltype(&ncclGetUniqueId) GetUniqueId = nullptr;
   decltype(&ncclCommInitRank) CommInitRank = nullptr;
-  decltype(&ncclCommInitAll) CommInitAll = nullptr;
   decltype(&ncclCommDestroy) CommDestroy = nullptr;
   decltype(&ncclAllGather) AllGather = nullptr;
   decltype(&ncclGroupStart) GroupStart = nullptr;
@@ -54,7 +53,6 @@ NcclApi* nccl_api() {
   if (!api.field) api.err = std::string("missing NCCL symbol ") + sym;
   LOAD(GetUniqueId, "ncclGetUniqueId")
   LOAD(CommInitRank, "ncclCommInitRank")
-  LOAD(CommInitAll, "ncclCommInitAll")
   LOAD(CommDestroy, "ncclCommDestroy")
   LOAD(AllGather, "ncclAllGather")
   LOAD(GroupStart, "ncclGroupStart")
@@ -201,27 +199,6 @@ int ecdna_b200_comm_init(ecdna_b200_ctx* ctx, const uint8_t id[ECDNA_B200_COMM_I
     return fail(ctx, ECDNA_B200_ERR_COMM, std::string("ncclCommInitRank: ") + api->GetErrorString(r));
   }
   ctx->comm = c;
-  return ECDNA_B200_OK;
-}
-
-int ecdna_b200_comm_init_all(ecdna_b200_ctx* const* ctxs, int n) {
-  if (!ctxs || n < 1) return ECDNA_B200_ERR_BAD_PARAMS;
-  ecdna_b200_ctx* ctx = ctxs[0];
-  NcclApi* api = nccl_api();
-  if (!api->err.empty()) return fail(ctx, ECDNA_B200_ERR_COMM, api->err);
-  int devs[64];
-  ncclComm_t comms[64];
-  if (n > 64) return fail(ctx, ECDNA_B200_ERR_BAD_PARAMS, "at most 64 devices");
-  for (int i = 0; i < n; ++i) devs[i] = ctxs[i]->device;
-  NC(api->CommInitAll(comms, n, devs));
-  for (int i = 0; i < n; ++i) {
-    if (ctxs[i]->comm) { api->CommDestroy(ctxs[i]->comm->comm); delete ctxs[i]->comm; }
-    ecdna_b200_comm* c = new ecdna_b200_comm();
-    c->comm = comms[i];
-    c->rank = i;
-    c->world = n;
-    ctxs[i]->comm = c;
-  }
   return ECDNA_B200_OK;
 }
 

@@ -80,53 +80,6 @@ void target_stats(const std::vector<uint64_t>& h, float* mean, float* ent, float
   *ent = e;
 }
 
-size_t col_bytes(int c, const ecdna_b200_params_t* p, uint32_t stride) {
-  switch (c) {
-    case C_STOP: case C_KMAX: case C_SNAPCOUNT: case C_DYNCOUNT: case C_NDIV: case C_NDEATH: return 4;
-    case C_NMINUS: case C_NPLUS: case C_NEVENTS: case C_HASH: case C_CHAIN: case C_SUMK: return 8;
-    case C_TIME: case C_MEAN: case C_FREQ: case C_ENT: case C_VAR: return 4;
-    case C_ABCD: return 16;
-    case C_ABCA: return 1;
-    case C_HIST: return (size_t)stride * 4;
-    case C_SNAPCELLS: return (size_t)p->n_snapshots * 8;
-    case C_SNAPTIME: return (size_t)p->n_snapshots * 4;
-    case C_SNAPHIST: return (size_t)p->n_snapshots * stride * 4;
-    case C_DYN: return (size_t)p->dyn_points * 5 * 4;
-    case C_SUBHIST: return (size_t)p->n_subsamples * stride * 4;
-  }
-  return 0;
-}
-void** col_slot(ecdna_b200_results_t* r, int c) {
-  switch (c) {
-    case C_STOP: return (void**)&r->stop_reason;
-    case C_NMINUS: return (void**)&r->nminus;
-    case C_NPLUS: return (void**)&r->nplus;
-    case C_TIME: return (void**)&r->time;
-    case C_NEVENTS: return (void**)&r->n_events;
-    case C_KMAX: return (void**)&r->kmax;
-    case C_MEAN: return (void**)&r->mean;
-    case C_FREQ: return (void**)&r->frequency;
-    case C_ENT: return (void**)&r->entropy;
-    case C_VAR: return (void**)&r->variance;
-    case C_ABCD: return (void**)&r->abc_distance;
-    case C_ABCA: return (void**)&r->abc_accept;
-    case C_HASH: return (void**)&r->hash;
-    case C_CHAIN: return (void**)&r->chain;
-    case C_HIST: return (void**)&r->hist;
-    case C_SNAPCOUNT: return (void**)&r->snap_count;
-    case C_SNAPCELLS: return (void**)&r->snap_cells;
-    case C_SNAPTIME: return (void**)&r->snap_time;
-    case C_SNAPHIST: return (void**)&r->snap_hist;
-    case C_DYNCOUNT: return (void**)&r->dyn_count;
-    case C_DYN: return (void**)&r->dyn;
-    case C_SUMK: return (void**)&r->sum_k;
-    case C_NDIV: return (void**)&r->n_div;
-    case C_NDEATH: return (void**)&r->n_death;
-    case C_SUBHIST: return (void**)&r->sub_hist;
-  }
-  return nullptr;
-}
-
 int validate(ecdna_b200_ctx* ctx, const ecdna_b200_params_t* p, uint64_t n_runs) {
   if (!p) return fail(ctx, ECDNA_B200_ERR_BAD_PARAMS, "params is NULL");
   if (p->abi_version != ECDNA_B200_ABI_VERSION) return fail(ctx, ECDNA_B200_ERR_BAD_PARAMS, "abi_version mismatch");

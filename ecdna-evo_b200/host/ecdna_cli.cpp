@@ -6,6 +6,11 @@
 // (src/process.rs:31-55) with the names of src/lib.rs:27-45: one JSON histogram per triggered
 // snapshot, one for the final state, one per --subsamples size.
 //
+// The index range runs on every visible B200 (ecdna_b200_multi_run: one host thread and context per GPU),
+// in chunks, so that host memory is O(chunk) whatever --runs is; the files of a chunk are written while the
+// next one is simulated.  `ecdna abc --target FILE.json ...` is the front end of the reference's removed ABC
+// binary (abc.md:10-55): prior draws over (b1, d0, d1), one run per draw, abc.csv with every draw.
+//
 // The reference is Rust; no Rust toolchain exists in this image, so the host side above the C ABI is
 // C++ (INTEGRATION.md shows the Rust binding a maintainer would add instead of this file).
 #include <sys/stat.h>
@@ -19,6 +24,7 @@
 #include <cstring>
 #include <ctime>
 #include <fstream>
+#include <future>
 #include <map>
 #include <sstream>
 #include <string>
@@ -50,8 +56,15 @@ struct Cli {
   bool summaries = false;  // mean / frequency / entropy of the final distribution
   bool dynamics = false;   // 300 samples of (nminus, nplus, mean, variance, entropy) every 0.1 time units
   // engine knobs (not in the reference)
-  int device = 0;
+  std::vector<int> devices;  // empty = every visible B200
+  uint64_t chunk = 0;        // replicates per library call (0 = sized for ~2 GiB of host buffers per GPU)
   uint32_t tile_width = 0, state_mode = 0;
+  uint32_t bd_count_mode = 0;  // 0: --cells counts cells; 1: sosa's literal population sum
+  // `ecdna abc` (abc.md:10-55)
+  bool abc = false;
+  std::string target;
+  float b1_range[2] = {1.f, 2.f}, d0_range[2] = {0.f, 0.5f}, d1_range[2] = {0.f, 0.5f};
+  float thresholds[4] = {0.05f, 0.1f, 0.1f, 0.1f};
 };
 
 [[noreturn]] void die(const std::string& msg) {
@@ -85,8 +98,13 @@ void usage() {
       "  -v, --verbosity...\n"
       "      --summaries                  also write <cells>cells/{mean,frequency,entropy}/<t>years/<name>.json\n"
       "      --dynamics                   also write <cells>cells/dynamics/<t>years/<name>.json (300 x 0.1)\n"
-      "      --device <N>  --tile-width <4|8|16|32>  --state <auto|smem|hbm>   (B200 engine knobs)\n"
-      "  -h, --help\n  -V, --version");
+      "      --devices <all|N,N,...>      GPUs to use [default: all]   --chunk <N> replicates per library call\n"
+      "      --tile-width <1|2|4|8|16|32>  --state <auto|smem|hbm>   (B200 engine knobs)\n"
+      "      --bd-count-mode <cells|sosa-sum>  what --cells counts for the birth-death process [default: cells]\n"
+      "  -h, --help\n  -V, --version\n\n"
+      "ABC (abc.md): ecdna abc --target <FILE.json> [-r draws] [--b1-range lo,hi] [--d0-range lo,hi] [--d1-range lo,hi]\n"
+      "              [--thresholds ks,mean,entropy,frequency] [--cells N] [--seed S] [--initial FILE] <DIR>\n"
+      "              writes <DIR>/abc.csv (every draw) and <DIR>/abc_accepted.csv");
 }
 
 std::vector<uint64_t> parse_list(const std::string& v) {
@@ -110,7 +128,15 @@ Cli parse(int argc, char** argv) {
     if (i + 1 >= argc) die("a value is required for '" + name + "' but none was supplied");
     return argv[++i];
   };
-  for (int i = 1; i < argc; ++i) {
+  auto pair_of = [&](const std::string& v, float* out) {
+    const size_t comma = v.find(',');
+    if (comma == std::string::npos) die("invalid range '" + v + "': expected lo,hi");
+    out[0] = std::strtof(v.substr(0, comma).c_str(), nullptr);
+    out[1] = std::strtof(v.substr(comma + 1).c_str(), nullptr);
+  };
+  int first = 1;
+  if (argc > 1 && std::string(argv[1]) == "abc") { c.abc = true; first = 2; }
+  for (int i = first; i < argc; ++i) {
     std::string a = argv[i], val;
     const size_t eq = a.find('=');
     bool has_eq = false;
@@ -135,7 +161,27 @@ Cli parse(int argc, char** argv) {
     else if (a == "--snapshots") { c.has_snapshots = true; if (has_eq) c.snapshots = parse_list(val); }
     else if (a == "--summaries") c.summaries = true;
     else if (a == "--dynamics") c.dynamics = true;
-    else if (a == "--device") c.device = std::atoi(value().c_str());
+    else if (a == "--device" || a == "--devices") {
+      const std::string v = value();
+      if (v != "all") for (uint64_t d : parse_list(v)) c.devices.push_back((int)d);
+    }
+    else if (a == "--chunk") c.chunk = std::strtoull(value().c_str(), nullptr, 10);
+    else if (a == "--bd-count-mode") {
+      const std::string v = value();
+      if (v != "cells" && v != "sosa-sum") die("invalid value '" + v + "' for '--bd-count-mode' [possible values: cells, sosa-sum]");
+      c.bd_count_mode = v == "sosa-sum" ? 1u : 0u;
+    }
+    else if (c.abc && a == "--target") c.target = value();
+    else if (c.abc && a == "--b1-range") pair_of(value(), c.b1_range);
+    else if (c.abc && a == "--d0-range") pair_of(value(), c.d0_range);
+    else if (c.abc && a == "--d1-range") pair_of(value(), c.d1_range);
+    else if (c.abc && a == "--thresholds") {
+      std::stringstream ss(value());
+      std::string tok;
+      int j = 0;
+      while (std::getline(ss, tok, ',') && j < 4) c.thresholds[j++] = std::strtof(tok.c_str(), nullptr);
+      if (j != 4) die("--thresholds needs four values: ks,mean,entropy,frequency");
+    }
     else if (a == "--tile-width") c.tile_width = (uint32_t)std::atoi(value().c_str());
     else if (a == "--state") {
       const std::string s = value();
@@ -148,6 +194,7 @@ Cli parse(int argc, char** argv) {
     else die("unexpected argument '" + a + "' found");
   }
   if (!have_path) die("the following required arguments were not provided:\n  <DIR>");
+  if (c.abc && c.target.empty()) die("the following required arguments were not provided:\n  --target <FILE.json>");
   if (c.has_years && c.has_cells) die("the argument '--years <YEARS>' cannot be used with '--cells <CELLS>'");
   if (c.debug && (c.has_years || c.has_cells || c.sequential || runs_given || verb_given))
     die("the argument '--debug' cannot be used with one or more of the other specified arguments");
@@ -280,6 +327,65 @@ const char* kStopNames[] = {"NoIndividualsLeft", "MaxItersReached", "MaxTimeReac
                             "AbsorbingStateReached", "CopyNumberOverflow", "HistogramOverflow", "ReplayExhausted",
                             "ReplayInconsistent"};
 
+// `ecdna abc`: the removed ABC binary of the reference (abc.md:10-55).  One run per prior draw over
+// (f1 = b1, d2 = d0, d1), the four distances to the target distribution from the kernel's fused epilogue, and
+// abc.csv with EVERY draw ("save all, filter later", abc.md:57-71) in the column order of abc.md:38-55;
+// abc_accepted.csv holds the draws within the thresholds.
+int run_abc(const Cli& c, ecdna_b200_multi* gpus, ecdna_b200_params_t p, uint64_t idx_begin, uint64_t draws,
+            const std::map<uint32_t, uint64_t>& init) {
+  const std::map<uint32_t, uint64_t> tgt = load_json_hist(c.target);
+  std::vector<uint64_t> target((size_t)tgt.rbegin()->first + 1, 0);
+  for (auto& kv : tgt) target[kv.first] = kv.second;
+  uint64_t init_cells = 0, init_copies = 0;
+  for (auto& kv : init) { init_cells += kv.second; init_copies += (uint64_t)kv.first * kv.second; }
+  const double init_mean = init_cells ? (double)init_copies / (double)init_cells : 0.0;
+  p.abc_enabled = 1;
+  p.abc_target_hist = target.data();
+  p.abc_target_len = (uint32_t)target.size();
+  for (int j = 0; j < 4; ++j) p.abc_thresholds[j] = c.thresholds[j];
+  p.hist_stride = 64;  // (the distributions themselves are not written)
+  mkdirs(c.path);
+  std::ofstream all(c.path + "/abc.csv"), acc(c.path + "/abc_accepted.csv");
+  if (!all || !acc) { std::fprintf(stderr, "Cannot create %s/abc.csv\n", c.path.c_str()); return 101; }
+  const char* header = "parental_idx,idx,timepoint,seed,ecdna,mean,entropy,f1,f2,d1,d2,cells,tumour_cells,init_mean,init_cells,init_copies\n";
+  all << header;
+  acc << header;
+  ecdna_b200_ctx* prior_ctx = nullptr;  // prior draws: Philox keyed (seed, draw index), on the first GPU
+  if (ecdna_b200_create(c.devices.empty() ? 0 : c.devices[0], &prior_ctx) != ECDNA_B200_OK) return 101;
+  const uint64_t chunk = c.chunk ? c.chunk : 262144ull * (uint64_t)ecdna_b200_multi_device_count(gpus);
+  uint64_t n_acc = 0;
+  for (uint64_t first = 0; first < draws; first += chunk) {
+    const uint64_t n = std::min<uint64_t>(chunk, draws - first);
+    std::vector<float> rates(n * 4), dist(n * 4);
+    std::vector<uint8_t> accept(n);
+    std::vector<uint64_t> nminus(n), nplus(n);
+    std::vector<uint32_t> stop(n);
+    int rc = ecdna_b200_abc_draw_priors(prior_ctx, c.seed, idx_begin + first, n, c.b0, c.b1_range, c.d0_range, c.d1_range, rates.data());
+    if (rc != ECDNA_B200_OK) { std::fprintf(stderr, "prior draws: %s\n", ecdna_b200_last_error(prior_ctx)); return 101; }
+    p.rates_per_run = rates.data();
+    ecdna_b200_results_t r;
+    std::memset(&r, 0, sizeof r);
+    r.stop_reason = stop.data(); r.nminus = nminus.data(); r.nplus = nplus.data();
+    r.abc_distance = dist.data(); r.abc_accept = accept.data();
+    rc = ecdna_b200_multi_run(gpus, &p, idx_begin + first, n, &r);
+    if (rc != ECDNA_B200_OK) { std::fprintf(stderr, "ecdna_b200_multi_run: %s\n", ecdna_b200_multi_last_error(gpus)); return 101; }
+    char line[512];
+    for (uint64_t i = 0; i < n; ++i) {
+      const unsigned long long tumour = nminus[i] + nplus[i];
+      // abc.md:44-52: f1/d1 belong to the cells WITH ecDNA, f2/d2 to the cells without
+      std::snprintf(line, sizeof line, ",%llu,0,%llu,%.9g,%.9g,%.9g,%.9g,%.9g,%.9g,%.9g,%llu,%llu,%.9g,%llu,%llu\n",
+                    (unsigned long long)(idx_begin + first + i), (unsigned long long)c.seed, (double)dist[4 * i], (double)dist[4 * i + 1],
+                    (double)dist[4 * i + 2], (double)rates[4 * i + 1], (double)rates[4 * i], (double)rates[4 * i + 3],
+                    (double)rates[4 * i + 2], tumour, tumour, init_mean, (unsigned long long)init_cells, (unsigned long long)init_copies);
+      all << line;
+      if (accept[i]) { acc << line; ++n_acc; }
+    }
+  }
+  ecdna_b200_destroy(prior_ctx);
+  std::printf("%llu of %llu draws within the thresholds\n", (unsigned long long)n_acc, (unsigned long long)draws);
+  return 0;
+}
+
 }  // namespace
 
 int main(int argc, char** argv) {
@@ -327,12 +433,13 @@ int main(int argc, char** argv) {
 
   std::printf("%s Starting the simulation\n", utc_now().c_str());  // main.rs:53
 
-  ecdna_b200_ctx* ctx = nullptr;
-  int rc = ecdna_b200_create(c.device, &ctx);
+  ecdna_b200_multi* gpus = nullptr;
+  int rc = ecdna_b200_multi_create(c.devices.empty() ? nullptr : c.devices.data(), (int)c.devices.size(), &gpus);
   if (rc != ECDNA_B200_OK) {
-    std::fprintf(stderr, "ecdna_b200_create failed with status %d (no B200 visible? this backend has no CPU path)\n", rc);
+    std::fprintf(stderr, "ecdna_b200_multi_create failed with status %d (no B200 visible? this backend has no CPU path)\n", rc);
     return 101;
   }
+  const int n_gpus = ecdna_b200_multi_device_count(gpus);
   ecdna_b200_params_t p;
   std::memset(&p, 0, sizeof p);
   p.abi_version = ECDNA_B200_ABI_VERSION;
@@ -340,88 +447,123 @@ int main(int argc, char** argv) {
   p.segregation = seg;
   p.max_cells = cells; p.max_iter = kMaxIter; p.max_time = (float)years;  // clap_app.rs:204-209
   p.seed = c.seed;
+  p.bd_count_mode = c.bd_count_mode;
   p.n_init = (uint32_t)init_k.size(); p.init_k = init_k.data(); p.init_c = init_c.data();
-  p.n_snapshots = (uint32_t)snapshots.size(); p.snapshot_cells = snapshots.empty() ? nullptr : snapshots.data();
   p.tile_width = c.tile_width; p.state_mode = c.state_mode;
+  const uint64_t idx_begin = c.seed * 10;  // main.rs:214
+  if (c.abc) {
+    const int arc = run_abc(c, gpus, p, idx_begin, runs, init);
+    ecdna_b200_multi_destroy(gpus);
+    if (arc == 0) std::printf("%s End simulation\n", utc_now().c_str());
+    return arc;
+  }
+  p.n_snapshots = (uint32_t)snapshots.size(); p.snapshot_cells = snapshots.empty() ? nullptr : snapshots.data();
   if (c.has_subsamples && !c.subsamples.empty()) {  // main.rs:110-123, drawn on the device
     p.n_subsamples = (uint32_t)c.subsamples.size();
     p.subsample_cells = c.subsamples.data();
   }
-  uint32_t stride = 1024;
-
-  const uint64_t idx_begin = c.seed * 10;  // main.rs:214
-  std::vector<uint32_t> stop(runs), kmax(runs), snap_count(runs), hist, snap_hist, sub_hist;
-  std::vector<uint64_t> nminus(runs), nplus(runs), snap_cells(runs * snapshots.size());
-  std::vector<float> time(runs), snap_time(runs * snapshots.size());
   const uint32_t dyn_points = c.dynamics ? 300u : 0u;  // CHANGELOG.md:34-36
-  std::vector<float> mean(runs), freq(runs), entropy(runs), dyn((size_t)runs * dyn_points * 5);
-  std::vector<uint32_t> dyn_count(runs);
   p.dyn_points = dyn_points;
   p.dyn_dt = 0.1f;
-  for (int attempt = 0; attempt < 2; ++attempt) {
-    p.hist_stride = stride;
-    hist.assign((size_t)runs * stride, 0);
-    snap_hist.assign((size_t)runs * snapshots.size() * stride, 0);
-    sub_hist.assign((size_t)runs * p.n_subsamples * stride, 0);
-    ecdna_b200_results_t r;
-    std::memset(&r, 0, sizeof r);
-    r.stop_reason = stop.data(); r.nminus = nminus.data(); r.nplus = nplus.data(); r.time = time.data();
-    r.kmax = kmax.data(); r.hist = hist.data();
-    if (!snapshots.empty()) { r.snap_count = snap_count.data(); r.snap_cells = snap_cells.data(); r.snap_time = snap_time.data(); r.snap_hist = snap_hist.data(); }
-    if (c.summaries) { r.mean = mean.data(); r.frequency = freq.data(); r.entropy = entropy.data(); }
-    if (c.dynamics) { r.dyn = dyn.data(); r.dyn_count = dyn_count.data(); }
-    if (p.n_subsamples) r.sub_hist = sub_hist.data();
-    rc = ecdna_b200_run(ctx, &p, idx_begin, runs, &r);
-    if (rc != ECDNA_B200_OK) { std::fprintf(stderr, "ecdna_b200_run: %s\n", ecdna_b200_last_error(ctx)); return 101; }
-    uint32_t top = 0;
-    for (uint64_t i = 0; i < runs; ++i) top = std::max(top, kmax[i]);
-    if (top < stride) break;
-    stride = ((top + 1 + 1023) / 1024) * 1024;  // histograms were truncated: run again with room for them
-  }
 
-  for (uint64_t i = 0; i < runs; ++i) {
-    const uint64_t idx = idx_begin + i;
-    const std::string filename = make_filename(c, birth_death, d0, d1, idx);
-    const uint32_t code = stop[i] & 0xFFu;
-    if (code == ECDNA_B200_STOP_COPY_OVERFLOW) {  // proliferation.rs:63-67 panics: the reference aborts here
-      std::fprintf(stderr, "Overflow while segregating DNA into two daughter cells (idx %llu)\n", (unsigned long long)idx);
-      return 101;
+  // The index range goes through the library in chunks (host memory is O(chunk), whatever --runs is); the
+  // files of a chunk are written while the next chunk is simulated.
+  uint32_t stride = 1024;
+  const size_t n_snap = snapshots.size();
+  auto per_replicate_bytes = [&](uint32_t st) { return (size_t)(1 + n_snap + p.n_subsamples) * st * 4 + (size_t)dyn_points * 20 + 64; };
+  uint64_t chunk = c.chunk ? c.chunk : std::max<uint64_t>(1024, std::min<uint64_t>(65536, (2ull << 30) / per_replicate_bytes(stride))) * (uint64_t)n_gpus;
+  struct Buffers {
+    std::vector<uint32_t> stop, kmax, snap_count, hist, snap_hist, sub_hist, dyn_count;
+    std::vector<uint64_t> nminus, nplus, snap_cells;
+    std::vector<float> time, snap_time, mean, freq, entropy, dyn;
+    uint64_t first = 0, n = 0;
+    uint32_t stride = 0;
+  } buf[2];
+  auto simulate = [&](Buffers& b, uint64_t first, uint64_t n) -> int {
+    b.first = first; b.n = n;
+    b.stop.assign(n, 0); b.kmax.assign(n, 0); b.snap_count.assign(n, 0); b.dyn_count.assign(n, 0);
+    b.nminus.assign(n, 0); b.nplus.assign(n, 0); b.time.assign(n, 0.f);
+    b.snap_cells.assign(n * n_snap, 0); b.snap_time.assign(n * n_snap, 0.f);
+    b.mean.assign(n, 0.f); b.freq.assign(n, 0.f); b.entropy.assign(n, 0.f); b.dyn.assign((size_t)n * dyn_points * 5, 0.f);
+    for (int attempt = 0; attempt < 2; ++attempt) {
+      p.hist_stride = stride;
+      b.stride = stride;
+      b.hist.assign((size_t)n * stride, 0);
+      b.snap_hist.assign((size_t)n * n_snap * stride, 0);
+      b.sub_hist.assign((size_t)n * p.n_subsamples * stride, 0);
+      ecdna_b200_results_t r;
+      std::memset(&r, 0, sizeof r);
+      r.stop_reason = b.stop.data(); r.nminus = b.nminus.data(); r.nplus = b.nplus.data(); r.time = b.time.data();
+      r.kmax = b.kmax.data(); r.hist = b.hist.data();
+      if (n_snap) { r.snap_count = b.snap_count.data(); r.snap_cells = b.snap_cells.data(); r.snap_time = b.snap_time.data(); r.snap_hist = b.snap_hist.data(); }
+      if (c.summaries) { r.mean = b.mean.data(); r.frequency = b.freq.data(); r.entropy = b.entropy.data(); }
+      if (c.dynamics) { r.dyn = b.dyn.data(); r.dyn_count = b.dyn_count.data(); }
+      if (p.n_subsamples) r.sub_hist = b.sub_hist.data();
+      const int rc2 = ecdna_b200_multi_run(gpus, &p, idx_begin + first, n, &r);
+      if (rc2 != ECDNA_B200_OK) { std::fprintf(stderr, "ecdna_b200_multi_run: %s\n", ecdna_b200_multi_last_error(gpus)); return 101; }
+      uint32_t top = 0;
+      for (uint64_t i = 0; i < n; ++i) top = std::max(top, b.kmax[i]);
+      if (top < stride) break;
+      stride = ((top + 1 + 1023) / 1024) * 1024;  // histograms were truncated: run again with room for them
     }
-    for (uint32_t sidx = 0; sidx < snap_count[i] && !snapshots.empty(); ++sidx) {
-      const size_t o = (size_t)i * snapshots.size() + sidx;
-      if (verbosity > 0) std::printf("saving state for timepoint at time %s with cells %llu \n", rust_f32_to_string(snap_time[o]).c_str(), (unsigned long long)snap_cells[o]);
-      save(c, filename, snap_time[o], snap_hist.data() + o * stride, stride, verbosity);
-    }
-    save(c, filename, time[i], hist.data() + (size_t)i * stride, stride, verbosity);  // main.rs:100-109
-    if (c.summaries) {
-      const uint64_t cells_now = nminus[i] + nplus[i];
-      const std::pair<const char*, float> m[] = {{"mean", mean[i]}, {"frequency", freq[i]}, {"entropy", entropy[i]}};
-      for (auto& kv : m) {
-        std::ofstream f(measurement_path(c, cells_now, time[i], kv.first, filename));
-        f << rust_f32_to_string(kv.second);
+    return 0;
+  };
+  auto write_files = [&](const Buffers& b) -> int {
+    const uint32_t st = b.stride;
+    for (uint64_t i = 0; i < b.n; ++i) {
+      const uint64_t idx = idx_begin + b.first + i;
+      const std::string filename = make_filename(c, birth_death, d0, d1, idx);
+      const uint32_t code = b.stop[i] & 0xFFu;
+      if (code == ECDNA_B200_STOP_COPY_OVERFLOW) {  // proliferation.rs:63-67 panics: the reference aborts here
+        std::fprintf(stderr, "Overflow while segregating DNA into two daughter cells (idx %llu)\n", (unsigned long long)idx);
+        return 101;
       }
-    }
-    if (c.dynamics) {
-      std::ofstream f(measurement_path(c, nminus[i] + nplus[i], time[i], "dynamics", filename));
-      const char* names[5] = {"nminus", "nplus", "mean", "variance", "entropy"};
-      f << "{\"dt\":0.1";
-      for (int q = 0; q < 5; ++q) {
-        f << ",\"" << names[q] << "\":[";
-        for (uint32_t j = 0; j < dyn_count[i]; ++j) {
-          if (j) f << ",";
-          f << rust_f32_to_string(dyn[((size_t)i * dyn_points + j) * 5 + q]);
+      for (uint32_t sidx = 0; sidx < b.snap_count[i] && n_snap; ++sidx) {
+        const size_t o = (size_t)i * n_snap + sidx;
+        if (verbosity > 0) std::printf("saving state for timepoint at time %s with cells %llu \n", rust_f32_to_string(b.snap_time[o]).c_str(), (unsigned long long)b.snap_cells[o]);
+        save(c, filename, b.snap_time[o], b.snap_hist.data() + o * st, st, verbosity);
+      }
+      save(c, filename, b.time[i], b.hist.data() + (size_t)i * st, st, verbosity);  // main.rs:100-109
+      if (c.summaries) {
+        const uint64_t cells_now = b.nminus[i] + b.nplus[i];
+        const std::pair<const char*, float> m[] = {{"mean", b.mean[i]}, {"frequency", b.freq[i]}, {"entropy", b.entropy[i]}};
+        for (auto& kv : m) {
+          std::ofstream f(measurement_path(c, cells_now, b.time[i], kv.first, filename));
+          f << rust_f32_to_string(kv.second);
         }
-        f << "]";
       }
-      f << "}";
+      if (c.dynamics) {
+        std::ofstream f(measurement_path(c, b.nminus[i] + b.nplus[i], b.time[i], "dynamics", filename));
+        const char* names[5] = {"nminus", "nplus", "mean", "variance", "entropy"};
+        f << "{\"dt\":0.1";
+        for (int q = 0; q < 5; ++q) {
+          f << ",\"" << names[q] << "\":[";
+          for (uint32_t j = 0; j < b.dyn_count[i]; ++j) {
+            if (j) f << ",";
+            f << rust_f32_to_string(b.dyn[((size_t)i * dyn_points + j) * 5 + q]);
+          }
+          f << "]";
+        }
+        f << "}";
+      }
+      for (uint32_t j = 0; j < p.n_subsamples; ++j)  // main.rs:110-123: one file per --subsamples size
+        save(c, filename, b.time[i], b.sub_hist.data() + ((size_t)i * p.n_subsamples + j) * st, st, verbosity);
+      if (verbosity > 0)  // main.rs:205-210
+        std::printf("stop reason: %s\nnminus, nplus: [\n    %llu,\n    %llu,\n]\ntime: %s\n", kStopNames[code > 8 ? 8 : code],
+                    (unsigned long long)b.nminus[i], (unsigned long long)b.nplus[i], rust_f32_to_string(b.time[i]).c_str());
     }
-    for (uint32_t j = 0; j < p.n_subsamples; ++j)  // main.rs:110-123: one file per --subsamples size
-      save(c, filename, time[i], sub_hist.data() + ((size_t)i * p.n_subsamples + j) * stride, stride, verbosity);
-    if (verbosity > 0)  // main.rs:205-210
-      std::printf("stop reason: %s\nnminus, nplus: [\n    %llu,\n    %llu,\n]\ntime: %s\n", kStopNames[code > 8 ? 8 : code],
-                  (unsigned long long)nminus[i], (unsigned long long)nplus[i], rust_f32_to_string(time[i]).c_str());
+    return 0;
+  };
+  int status = 0, cur = 0;
+  std::future<int> writer;
+  for (uint64_t first = 0; first < runs && status == 0; first += chunk, cur ^= 1) {
+    status = simulate(buf[cur], first, std::min<uint64_t>(chunk, runs - first));
+    if (writer.valid()) { const int w = writer.get(); if (status == 0) status = w; }
+    if (status == 0) writer = std::async(std::launch::async, write_files, std::cref(buf[cur]));
   }
-  ecdna_b200_destroy(ctx);
+  if (writer.valid()) { const int w = writer.get(); if (status == 0) status = w; }
+  ecdna_b200_multi_destroy(gpus);
+  if (status) return status;
   std::printf("%s End simulation\n", utc_now().c_str());  // main.rs:226
   return 0;
 }

@@ -251,6 +251,22 @@ int ecdna_b200_abc_draw_priors_device(ecdna_b200_ctx* ctx, uint64_t seed, uint64
 int ecdna_b200_compact_accepted(ecdna_b200_ctx* ctx, const uint8_t* accept_dev, uint64_t n_runs,
                                 uint32_t* accepted_idx_dev, uint32_t* n_accepted, void* cuda_stream);
 
+/* ---- several GPUs of one box from one process (the reference's rayon loop, main.rs:214-225) ----
+   The index range of a batch is cut into contiguous blocks, one per GPU, each driven by its own host
+   thread and context; the blocks' results are written into the caller's arrays at the block's offset, so
+   the outputs are identical to a one-GPU run of the same range.  devices == NULL / n_devices == 0: every
+   visible sm_100 device. */
+typedef struct ecdna_b200_multi ecdna_b200_multi;
+int ecdna_b200_multi_create(const int* devices, int n_devices, ecdna_b200_multi** out);
+void ecdna_b200_multi_destroy(ecdna_b200_multi* m);
+int ecdna_b200_multi_device_count(const ecdna_b200_multi* m);
+const char* ecdna_b200_multi_last_error(const ecdna_b200_multi* m);
+/* ecdna_b200_run over all GPUs of `m` (host buffers in and out; blocking) */
+int ecdna_b200_multi_run(ecdna_b200_multi* m, const ecdna_b200_params_t* params, uint64_t idx_begin, uint64_t n_runs,
+                         const ecdna_b200_results_t* results);
+/* times of the slowest block, counts summed over the blocks */
+int ecdna_b200_multi_get_timing(ecdna_b200_multi* m, ecdna_b200_timing_t* t);
+
 /* ---- the one exchange step of the path: all-gather of the accepted ABC draws (abc.md:57-78) ----
    A record is ECDNA_B200_ABC_REC_HEADER + rec_bins 32-bit words:
      [0..1] replicate index (lo, hi)   [2..5] b0, b1, d0, d1 (f32 bits)   [6..9] the four distances (f32 bits)
@@ -271,10 +287,9 @@ int ecdna_b200_abc_pack(ecdna_b200_ctx* ctx, const ecdna_b200_results_t* results
 /* Communicator over the GPUs that share a batch: NCCL (NVLink 5 / NVSwitch inside one box), loaded with
    dlopen("libnccl.so.2") on first use.  One process per GPU: rank 0 calls _unique_id, the caller gets
    the 128 bytes to every rank (MPI, the launcher's rendezvous, a file ...) and every rank calls _comm_init.
-   One process, several GPUs: _comm_init_all on the contexts.  ecdna_b200_destroy releases it. */
+   ecdna_b200_destroy releases it. */
 int ecdna_b200_comm_unique_id(uint8_t id[ECDNA_B200_COMM_ID_BYTES]);
 int ecdna_b200_comm_init(ecdna_b200_ctx* ctx, const uint8_t id[ECDNA_B200_COMM_ID_BYTES], int rank, int world);
-int ecdna_b200_comm_init_all(ecdna_b200_ctx* const* ctxs, int n);
 void ecdna_b200_comm_release(ecdna_b200_ctx* ctx);
 
 /* All-gather of the packed records: every rank contributes its count and a block of `capacity` records;

@@ -362,6 +362,27 @@ def test_uniform_level_replay_bit_exact(pkg, ctx, name):
         assert int(cut.stop[0]) == pkg.STOP_REPLAY_END and int(cut.n_events[0]) < refs[0].n_events
 
 
+def test_uniform_replay_overflow_reports_the_reference_state(pkg, ctx):
+    """k >= 32768 cannot double (proliferation.rs:63-67 panics with the cell already taken out at :57): the
+    uniform-level kernel, the histogram kernel and the oracle all stop there with the same state."""
+    o = pkg.SimulationOptions(b0=1.0, b1=1.0, cells=60, runs=3, initial={40000: 1, 3: 2}, save_snapshots=False)
+    streams, refs = [], []
+    for i in range(o.runs):
+        r = ob.run(oracle_opts(o, o.idx_begin + i, state=ob.STATE_VECTOR, rng=ob.RNG_RAND), hist_cap=65536, u64_cap=100_000)
+        streams.append(r.u64)
+        refs.append(r)
+    assert any(r.stop_reason == ob.STOP_COPY_OVERFLOW for r in refs)
+    offsets = np.zeros(o.runs + 1, dtype=np.uint64)
+    offsets[1:] = np.cumsum([len(s) for s in streams])
+    res = ctx.run(o, want=WANT[:12], replay_u64=np.concatenate(streams), replay_offsets=offsets, hist_stride=65536)
+    for i, ref in enumerate(refs):
+        assert_run_equal(res, i, ref, 65536)
+    # the native stream stops the same way (its own draws: only the stop code and the bookkeeping are compared)
+    nat = ctx.run(o, want=WANT, hist_stride=65536, digest=True)
+    for i in range(o.runs):
+        assert_run_equal(nat, i, ob.run(oracle_opts(o, o.idx_begin + i), hist_cap=65536), 65536)
+
+
 def test_replay_detects_inconsistency(pkg, ctx):
     o = pkg.SimulationOptions(runs=1, cells=200, save_snapshots=False)
     r = _vector_trace(o, o.idx_begin, ob.RNG_RAND)
@@ -546,3 +567,97 @@ def test_bad_params_are_errors(pkg, ctx):
         ctx.run(pkg.SimulationOptions(runs=1, initial={0: 0}, save_snapshots=False))
     with pytest.raises(pkg.EcdnaB200Error):
         ctx.run(pkg.SimulationOptions(runs=1, save_snapshots=False), tile_width=5)
+
+
+def _tree(root):
+    import os
+    out = {}
+    for d, _, files in os.walk(root):
+        for f in files:
+            p = os.path.join(d, f)
+            out[os.path.relpath(p, root)] = open(p).read()
+    return out
+
+
+def test_cli_chunks_and_devices_give_identical_files(pkg, tmp_path):
+    """main.rs:214-225 maps the whole index range over all workers: the CLI runs it on every visible GPU, in
+    chunks (host memory O(chunk)); the files do not depend on the chunk size or on the number of GPUs."""
+    import os
+    import subprocess
+    import torch
+    pkg.build()
+    exe = os.path.join(os.path.dirname(pkg.LIB_PATH), "host", "ecdna")
+    base = ["--b1", "1.3", "--d0", "0.1", "--d1", "0.1", "--cells", "400", "--runs", "23", "--seed", "3", "--subsamples=40",
+            "--summaries"]
+    trees = []
+    variants = [["--devices", "0"], ["--devices", "0", "--chunk", "5"], ["--chunk", "7"]]
+    if torch.cuda.device_count() >= 2:
+        variants.append(["--devices", "0,1", "--chunk", "8"])
+    for i, extra in enumerate(variants):
+        out = str(tmp_path / f"o{i}")
+        r = subprocess.run([exe] + base + extra + [out], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        trees.append(_tree(out))
+    assert len(trees[0]) >= 23 * 3
+    for t in trees[1:]:
+        assert t == trees[0]
+    # the literal sosa stop rule (population array [n-,n+,n-,n+] summed: half the size) is one flag away
+    out = str(tmp_path / "half")
+    r = subprocess.run([exe, "--d0", "0.1", "--cells", "400", "--runs", "2", "--snapshots=", "--bd-count-mode", "sosa-sum", out],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert all(p.startswith("200cells") for p in _tree(out))
+
+
+def test_multi_context_matches_single_context(pkg, ctx):
+    """ecdna_b200_multi_run: contiguous index blocks per GPU written at their offsets = the one-GPU result."""
+    o = pkg.SimulationOptions(b0=1.0, b1=1.2, d0=0.2, d1=0.1, cells=1500, runs=301, snapshots=[1, 100, 1500])
+    want = WANT + ("snap_count", "snap_cells", "snap_time", "snap_hist", "dyn", "dyn_count")
+    a = ctx.run(o, want=want, dyn_points=50, dyn_dt=0.2)
+    m = pkg.MultiContext()
+    b = m.run(o, want=want, dyn_points=50, dyn_dt=0.2)
+    assert b.timing.n_finished == 301 and b.timing.total_events == a.timing.total_events
+    for f in want:
+        x, y = getattr(a, f), getattr(b, f)
+        if x.dtype.kind == "f":
+            x, y = x.view(np.uint32), y.view(np.uint32)
+        np.testing.assert_array_equal(x, y, err_msg=f)
+    rates = ctx.abc_draw_priors(seed=1, idx_begin=o.idx_begin, n_runs=301)
+    c = ctx.run(o, want=("n_events", "nplus"), rates_per_run=rates)
+    d = m.run(o, want=("n_events", "nplus"), rates_per_run=rates)
+    np.testing.assert_array_equal(c.n_events, d.n_events)
+    m.close()
+
+
+def test_cli_abc_front_end(pkg, ctx, tmp_path):
+    """`ecdna abc --target FILE.json`: abc.csv with every draw in the column order of abc.md:38-55, distances
+    equal to the oracle's for the same prior draws, abc_accepted.csv = the rows within the thresholds."""
+    import csv
+    import json
+    import os
+    import subprocess
+    pkg.build()
+    exe = os.path.join(os.path.dirname(pkg.LIB_PATH), "host", "ecdna")
+    o = pkg.SimulationOptions(b0=1.0, b1=1.4, d0=0.2, d1=0.2, cells=2000, seed=7, save_snapshots=False)
+    target = ob.run(oracle_opts(o, 999), hist_cap=256).hist
+    tfile = tmp_path / "target.json"
+    tfile.write_text(json.dumps({str(k): int(c) for k, c in enumerate(target) if c}))
+    out = str(tmp_path / "abc")
+    thr = (0.2, 0.5, 0.5, 0.5)
+    r = subprocess.run([exe, "abc", "--target", str(tfile), "-r", "300", "--cells", "2000", "--seed", "7", "--chunk", "128",
+                        "--thresholds", ",".join(map(str, thr)), out], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    rows = list(csv.DictReader(open(os.path.join(out, "abc.csv"))))
+    assert list(rows[0].keys()) == pkg.ABC_FIELDS and len(rows) == 300
+    assert [int(x["idx"]) for x in rows] == list(range(70, 370))
+    rates = np.array([[x["f2"], x["f1"], x["d2"], x["d1"]] for x in rows], dtype=np.float32)  # b0, b1, d0, d1
+    np.testing.assert_array_equal(rates, ctx.abc_draw_priors(seed=7, idx_begin=70, n_runs=300))
+    ref = ob.abc_batch(oracle_opts(o, 0), 70, 300, rates, target, thr, 0, hist_cap=512)
+    got = np.array([[x["ecdna"], x["mean"], x["entropy"]] for x in rows], dtype=np.float32)
+    np.testing.assert_allclose(got, ref.distance[:, :3], rtol=1e-4, atol=1e-5)
+    acc = list(csv.DictReader(open(os.path.join(out, "abc_accepted.csv"))))
+    clear = np.abs(ref.distance - np.array(thr)[None, :]).min(axis=1) > 1e-4
+    want_acc = {70 + i for i in range(300) if ref.accept[i]}
+    got_acc = {int(x["idx"]) for x in acc}
+    assert {i for i in want_acc ^ got_acc if clear[i - 70]} == set() and 0 < len(acc) < 300
+    assert all(int(x["init_cells"]) == 1 and int(x["init_copies"]) == 1 for x in rows[:5])
