@@ -15,7 +15,7 @@ import os
 
 import numpy as np
 
-from .build import LIB_PATH, build  # noqa: F401
+from .build import LIB_PATH, build, build_debug  # noqa: F401
 from .shard import gather_accepted, rank_range  # noqa: F401
 from .abc import (ABC_FIELDS, REC_HEADER, abc_rows, decode_records, merge_gathered, record_words,  # noqa: F401
                   write_abc_csv)

@@ -47,6 +47,29 @@ def _stamp(target, sources, extra=""):
         f.write(_digest(sources, extra))
 
 
+def build_debug():
+    """libecdna_b200_dbg.so: the same sources with -DECDNA_DEBUG_BOUNDS (device-side asserts on every window
+    address, record index and output index).  Select it with ECDNA_B200_LIB=<path> (scripts/sanitize_cases.py)."""
+    out = os.path.join(PKG_DIR, "libecdna_b200_dbg.so")
+    units = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith(".cu")]
+    from concurrent.futures import ThreadPoolExecutor
+    os.makedirs(OBJ_DIR, exist_ok=True)
+
+    def one(src):
+        obj = os.path.join(OBJ_DIR, os.path.basename(src)[:-3] + ".dbg.o")
+        r = subprocess.run([_nvcc()] + NVCC_FLAGS + ["-DECDNA_DEBUG_BOUNDS", "-c", "-o", obj, src], capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
+        return obj
+
+    with ThreadPoolExecutor(max_workers=min(len(units), os.cpu_count() or 1)) as ex:
+        objs = list(ex.map(one, units))
+    r = subprocess.run([_nvcc()] + LINK_FLAGS + ["-o", out] + objs, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("nvcc (link) failed:\n" + r.stdout + r.stderr)
+    return out
+
+
 def build(force=False, verbose=False):
     """Compile csrc/*.cu into libecdna_b200.so and host/*.cpp into the `ecdna` CLI."""
     srcs = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC))] + [os.path.join(ROOT, "include", "ecdna_b200.h")]
