@@ -4,6 +4,7 @@
 // sm_100 device every entry point fails with ECDNA_B200_ERR_NO_DEVICE / ECDNA_B200_ERR_CUDA.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -153,8 +154,24 @@ int run_common(ecdna_b200_ctx* ctx, const ecdna_b200_params_t* p, uint64_t idx_b
   // (1-lane tiles draw 128 segregation bits per event inline and fit six warps per SM with a 256-bin window only)
   const bool lane_ok = native && k0max <= 16u && (p->smem_bins == 0 || p->smem_bins <= 256u) &&
                        p->state_mode != ECDNA_B200_STATE_HBM;
-  const uint32_t L = p->tile_width ? p->tile_width : default_tile_width(n_runs, ctx->sm_count, native, lane_ok);
-  const uint32_t default_bins = (L <= 4 && k0max <= 16u) ? 256u : 512u;
+  uint32_t L = p->tile_width ? p->tile_width : default_tile_width(n_runs, ctx->sm_count, native, lane_ok);
+  // Large initial copy numbers: the copy numbers of a growing population spread to roughly twice the largest
+  // initial one (measured: {2000: 1} reaches ~3100 at 1e5 cells, {10000: 1} ~12000), and a replicate that
+  // outgrows its window moves to the HBM launch, which is several times slower.  So the default window holds
+  // 2 k0 + 256 bins when that fits a block (4 warps, ~200 KB of shared memory), on wider tiles if need be.
+  uint32_t default_bins = (L <= 4 && k0max <= 16u) ? 256u : 512u;
+  if (k0max > 128u && p->smem_bins == 0 && p->state_mode != ECDNA_B200_STATE_HBM) {
+    const uint32_t want_bins = (2u * k0max + 256u + 127u) & ~127u;
+    auto fits = [](uint32_t lanes) -> uint32_t {  // bins per replicate a 4-warp block holds with tiles of `lanes`
+      const uint32_t r = 32u / lanes, sg = (r + 3u) / 4u;
+      return ((200u * 1024u / 16u - 128u * sg) / r) & ~127u;
+    };
+    // (a draw of 2k bits beyond the tile's own 128 (L - 1) needs the complete step, except on full-warp tiles,
+    //  whose straight-line step loops over the extra slots: measured 2.4x on {2000: 1})
+    if (!p->tile_width)
+      while (L < 32u && (fits(L) < want_bins || 128u * (L - 1u) < 4u * k0max)) L *= 2u;
+    default_bins = std::max(default_bins, std::min(want_bins, fits(L)));
+  }
   a.kcap_s = p->smem_bins ? ((p->smem_bins + 127u) & ~127u) : default_bins;  // bins come in rows of 4 x 32
   a.kcap_g = ((p->max_copies ? p->max_copies : 65535u) + 128u) & ~127u;
   if (a.kcap_g < a.kcap_s) a.kcap_g = a.kcap_s;
