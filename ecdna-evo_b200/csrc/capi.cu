@@ -19,11 +19,53 @@ using namespace ecdna;
 
 namespace {
 
-// phase 1: histogram in shared memory, tiles of L lanes; phase 2: parked replicates, histogram in HBM
+// ---- longest-expected-first order of a batch with per-run rates (ABC prior draws) ----
+// The replicates of such a batch differ several-fold in length: a draw with net growth rate r = b - d of its
+// dominant cell type takes about min(N, e^(rT)) (b + d) / r events to reach N cells or the time limit T.  A
+// launch that hands out the longest first ends with the short ones, which cuts the under-occupied tail of the
+// batch (decisive when 1e6 draws are spread over 8 GPUs).  Results do not depend on the order.
+constexpr uint32_t kLptBuckets = 1024;
+__device__ __forceinline__ uint32_t lpt_bucket(const float* r, float max_cells, float max_time) {
+  const float rp = r[1] - r[3], rm = r[0] - r[2];
+  const bool plus = rp >= rm;
+  const float net = plus ? rp : rm, tot = plus ? r[1] + r[3] : r[0] + r[2];
+  float cost = 1.0f;
+  if (net > 0.02f) cost = fminf(max_cells, __expf(fminf(net * max_time, 80.f))) * tot / net;
+  const int b = (int)(__log2f(fmaxf(cost, 1.0f)) * 24.0f);  // ~3 % steps
+  return kLptBuckets - 1u - (uint32_t)min(max(b, 0), (int)kLptBuckets - 1);  // bucket 0 = the longest
+}
+__global__ void lpt_count(const float* rates, uint32_t n, float max_cells, float max_time, uint32_t* hist) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) atomicAdd(hist + lpt_bucket(rates + 4 * (size_t)i, max_cells, max_time), 1u);
+}
+__global__ void lpt_scan(uint32_t* hist) {  // one block of kLptBuckets threads: exclusive scan in place
+  __shared__ uint32_t sh[kLptBuckets];
+  const uint32_t t = threadIdx.x;
+  sh[t] = hist[t];
+  __syncthreads();
+  for (uint32_t o = 1; o < kLptBuckets; o <<= 1) {
+    const uint32_t v = t >= o ? sh[t - o] : 0u;
+    __syncthreads();
+    sh[t] += v;
+    __syncthreads();
+  }
+  hist[t] = sh[t] - hist[t];
+}
+__global__ void lpt_scatter(const float* rates, uint32_t n, float max_cells, float max_time, uint32_t* cursor, uint32_t* order) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) order[atomicAdd(cursor + lpt_bucket(rates + 4 * (size_t)i, max_cells, max_time), 1u)] = i;
+}
+
+// phase 1: histogram in shared memory, tiles of L lanes; a replicate that outgrows its window is parked with
+// its state and continued by the next launch of the cascade: (1-lane tiles with a 128-bin window only) a second
+// shared-memory launch with 256 bins, then the launch with the histogram in HBM
 int launch_all(ecdna_b200_ctx* ctx, SsaArgs& a, cudaStream_t st, const ecdna_b200_params_t* p, uint32_t L, bool replay) {
   uint32_t grid = 0, bps = 0;
   ecdna_b200_timing_t& tm = ctx->timing;
+  uint32_t* const ctr = (uint32_t*)ctx->counters.p;  // [0] [1] [28]: queues of the three launches; [2] [3]: park counts
   CU(cudaEventRecord(ctx->ev_k0, st));
+  a.resume_count = nullptr;
+  a.work_counter = ctr;
   if (p->state_mode == ECDNA_B200_STATE_HBM) {
     a.park_list = nullptr;
     a.allow_park = 0;
@@ -47,15 +89,42 @@ int launch_all(ecdna_b200_ctx* ctx, SsaArgs& a, cudaStream_t st, const ecdna_b20
     tm.kernel_launches = 1;
     tm.tile_width = L;
     tm.block_threads = L == 1 ? (uint32_t)block_threads<1>() : (uint32_t)kBlockThreads;
+    tm.smem_bins = a.kcap_s;
     if (a.allow_park) {
+      // the next launch works through what this one parked
+      SsaArgs n = a;
+      n.resume_count = a.park_count; n.resume_list = a.park_list; n.resume_rec = a.park_rec;
+      n.resume_cap = a.park_cap; n.resume_kcap = a.kcap_s;
+      n.work_counter = ctr + 1;
+      n.ts_quantum = 0;
       uint32_t g2 = 0, b2 = 0;
-      rc = launch_hbm(ctx, a, st, replay, &g2, &b2);
+      if (L == 1 && a.kcap_s == 128) {
+        // 1-lane tiles run ten warps per SM with a 128-bin window (six with 256); the few replicates whose
+        // copy numbers pass 127 continue in a 256-bin launch of the same kernel, whose own leftovers go to HBM
+        const uint64_t cap2 = a.park_cap;
+        CU(ctx->park_list2.ensure((size_t)a.n_runs * 4));
+        CU(ctx->park_rec2.ensure((cap2 ? cap2 : 1) * (size_t)(kParkHdr + 32u + 256u) * 4));
+        n.kcap_s = 256;
+        if (n.kcap_g < n.kcap_s) n.kcap_g = n.kcap_s;
+        n.park_count = ctr + 3; n.park_list = (uint32_t*)ctx->park_list2.p; n.park_rec = (uint32_t*)ctx->park_rec2.p;
+        n.park_cap = (uint32_t)cap2;
+        rc = launch_smem<1>(ctx, n, st, replay, 0xFFFFFFFFu, &g2, &b2);
+        if (rc) return rc;
+        tm.kernel_launches += 1;
+        SsaArgs h = n;
+        h.resume_count = n.park_count; h.resume_list = n.park_list; h.resume_rec = n.park_rec;
+        h.resume_cap = n.park_cap; h.resume_kcap = n.kcap_s;
+        h.work_counter = ctr + 28;
+        n = h;
+      }
+      n.allow_park = 0;
+      rc = launch_hbm(ctx, n, st, replay, &g2, &b2);
       if (rc) return rc;
-      tm.kernel_launches = 2;
+      tm.kernel_launches += 1;
     }
   }
   CU(cudaEventRecord(ctx->ev_k1, st));
-  tm.smem_bins = a.kcap_s;
+  if (p->state_mode == ECDNA_B200_STATE_HBM) tm.smem_bins = a.kcap_s;
   tm.grid_blocks = grid;
   tm.blocks_per_sm = bps;
   return ECDNA_B200_OK;
@@ -160,6 +229,10 @@ int run_common(ecdna_b200_ctx* ctx, const ecdna_b200_params_t* p, uint64_t idx_b
   // outgrows its window moves to the HBM launch, which is several times slower.  So the default window holds
   // 2 k0 + 256 bins when that fits a block (4 warps, ~200 KB of shared memory), on wider tiles if need be.
   uint32_t default_bins = (L <= 4 && k0max <= 16u) ? 256u : 512u;
+  // (1-lane tiles with smem_bins = 128 run ten warps per SM instead of six and continue the replicates whose
+  //  copy numbers pass 127 in a 256-bin launch, see launch_all.  Measured on the C4 shape: +16 % while every SM
+  //  is full, +3 % over a whole 1e6-draw batch - the longer tail of a launch that holds more replicates eats
+  //  the rest - so it is not the default.)
   if (k0max > 128u && p->smem_bins == 0 && p->state_mode != ECDNA_B200_STATE_HBM) {
     const uint32_t want_bins = (2u * k0max + 256u + 127u) & ~127u;
     auto fits = [](uint32_t lanes) -> uint32_t {  // bins per replicate a 4-warp block holds with tiles of `lanes`
@@ -287,7 +360,7 @@ int run_common(ecdna_b200_ctx* ctx, const ecdna_b200_params_t* p, uint64_t idx_b
   a.out = dev;
   CU(ctx->counters.ensure(128));
   CU(cudaMemsetAsync(ctx->counters.p, 0, 128, st));
-  a.work_counter = (uint32_t*)ctx->counters.p;                              // [0], [1]: the two queues
+  a.work_counter = (uint32_t*)ctx->counters.p;                              // (launch_all assigns the queues)
   a.park_count = (uint32_t*)ctx->counters.p + 2;
   a.totals = (unsigned long long*)((char*)ctx->counters.p + kTotalsOffset);
   ctx->expect_finished = n_runs;
@@ -301,6 +374,19 @@ int run_common(ecdna_b200_ctx* ctx, const ecdna_b200_params_t* p, uint64_t idx_b
     a.park_cap = (uint32_t)cap;
   }
 
+  a.order = nullptr;
+  if (a.rates_per_run && native && n_runs >= 8192 && !(p->flags & ECDNA_B200_KEEP_ORDER)) {
+    const uint32_t n32 = (uint32_t)n_runs;
+    CU(ctx->order.ensure((size_t)n_runs * 4));
+    CU(ctx->order_hist.ensure(kLptBuckets * 4));
+    CU(cudaMemsetAsync(ctx->order_hist.p, 0, kLptBuckets * 4, st));
+    lpt_count<<<(n32 + 255) / 256, 256, 0, st>>>(a.rates_per_run, n32, (float)p->max_cells, p->max_time, (uint32_t*)ctx->order_hist.p);
+    lpt_scan<<<1, kLptBuckets, 0, st>>>((uint32_t*)ctx->order_hist.p);
+    lpt_scatter<<<(n32 + 255) / 256, 256, 0, st>>>(a.rates_per_run, n32, (float)p->max_cells, p->max_time, (uint32_t*)ctx->order_hist.p,
+                                                   (uint32_t*)ctx->order.p);
+    CU(cudaGetLastError());
+    a.order = (const uint32_t*)ctx->order.p;
+  }
   if (uniforms) {
     // the reference's own stream on the reference's own state layout: one thread per replicate
     UrArgs u{};
@@ -504,7 +590,7 @@ void ecdna_b200_destroy(ecdna_b200_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   ecdna_b200_comm_release(ctx);
   DevBuf* bufs[] = {&ctx->init_k, &ctx->init_c, &ctx->snap, &ctx->rates, &ctx->replay, &ctx->replay_off,
-                    &ctx->abc_cdf, &ctx->arena, &ctx->counters, &ctx->scratch, &ctx->park_list, &ctx->park_rec, &ctx->ts_ring, &ctx->ts_rec, &ctx->sub_sizes, &ctx->hist_tmp,
+                    &ctx->abc_cdf, &ctx->arena, &ctx->counters, &ctx->scratch, &ctx->park_list, &ctx->park_rec, &ctx->park_list2, &ctx->park_rec2, &ctx->order, &ctx->order_hist, &ctx->ts_ring, &ctx->ts_rec, &ctx->sub_sizes, &ctx->hist_tmp,
                     &ctx->cells, &ctx->zig, &ctx->pack_idx, &ctx->pack_out, &ctx->pack_cnt};
   for (DevBuf* b : bufs) b->release();
   for (auto& b : ctx->cols) b.release();

@@ -58,7 +58,7 @@ struct ecdna_b200_ctx {
   uint64_t expect_finished = 0;  // replicates the last run must have finished (checked in get_timing / run)
   std::string err;
   ecdna::DevBuf init_k, init_c, snap, rates, replay, replay_off, abc_cdf, arena, counters, scratch, park_list, park_rec,
-      cells, zig, ts_ring, ts_rec, sub_sizes, hist_tmp, pack_idx, pack_out, pack_cnt,
+      park_list2, park_rec2, order, order_hist, cells, zig, ts_ring, ts_rec, sub_sizes, hist_tmp, pack_idx, pack_out, pack_cnt,
       cols[ecdna::C_COUNT];
   size_t arena_words = 0, arena_kcap = 0;
   ecdna_b200_timing_t timing{};
@@ -272,7 +272,10 @@ int launch_smem(ecdna_b200_ctx* ctx, SsaArgs& a, cudaStream_t st, bool replay, u
 template <int L, bool REPLAY>
 int launch_smem_impl(ecdna_b200_ctx* ctx, SsaArgs& a, cudaStream_t st, uint32_t slice_events, uint32_t* grid,
                      uint32_t* bps) {
-  // the walk over the shared window is unrolled for the two common window sizes
+  // the walk over the shared window is unrolled for the common window sizes
+  if constexpr (L == 1 && !REPLAY) {
+    if (a.kcap_s == 128) return launch_kernel<L, false, REPLAY, 1>(ctx, a, st, a.n_runs, grid, bps, slice_events);
+  }
   if (!REPLAY && a.kcap_s == 256) return launch_kernel<L, false, REPLAY, 2>(ctx, a, st, a.n_runs, grid, bps, slice_events);
   if (!REPLAY && a.kcap_s == 512) return launch_kernel<L, false, REPLAY, 4>(ctx, a, st, a.n_runs, grid, bps, slice_events);
   return launch_kernel<L, false, REPLAY, 0>(ctx, a, st, a.n_runs, grid, bps, slice_events);

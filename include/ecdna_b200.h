@@ -77,6 +77,9 @@ enum { ECDNA_B200_STATE_AUTO = 0, ECDNA_B200_STATE_SMEM = 1, ECDNA_B200_STATE_HB
 
 /* ecdna_b200_params_t.flags */
 #define ECDNA_B200_WANT_DIGEST 0x1u /* maintain the histogram hash and the per-event chain digest */
+#define ECDNA_B200_KEEP_ORDER 0x2u  /* start the replicates in index order (default with per-run rates: the ones
+                                       expected to run longest first, which shortens the tail of the batch;
+                                       results never depend on the order) */
 
 /* one record of the replay stream: the decisions of one iteration of sosa::simulate, in the order
    the reference takes them (waiting time, event, cell picked, first daughter). 12 bytes. */

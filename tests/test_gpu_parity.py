@@ -92,7 +92,7 @@ def test_tile_widths_agree(pkg, ctx, name, tile_width):
         np.testing.assert_array_equal(a.time.view(np.uint32), b.time.view(np.uint32))
 
 
-@pytest.mark.parametrize("mode", ["hbm", "spill_resume", "spill_restart", "spill_mixed_l8"])
+@pytest.mark.parametrize("mode", ["hbm", "spill_resume", "spill_restart", "spill_mixed_l8", "lane_cascade", "lane_cascade_restart"])
 @pytest.mark.parametrize("name", ["wide", "wide_bd", "wide_initial", "huge_k"])
 def test_hbm_state_bit_exact(pkg, ctx, name, mode):
     """The HBM-resident histogram, and parking a replicate that outgrows shared memory (with its
@@ -100,14 +100,19 @@ def test_hbm_state_bit_exact(pkg, ctx, name, mode):
     o = pkg.SimulationOptions(runs=10, save_snapshots=False, **CASES[name])
     kw = {"hbm": dict(state_mode=pkg.STATE_HBM), "spill_resume": dict(smem_bins=128),
           "spill_restart": dict(smem_bins=128, spill_records=0xFFFFFFFF),
-          "spill_mixed_l8": dict(smem_bins=128, spill_records=3, tile_width=8)}[mode]
+          "spill_mixed_l8": dict(smem_bins=128, spill_records=3, tile_width=8),
+          # 1-lane tiles with a 128-bin window: parked replicates continue in a 256-bin launch, its leftovers in HBM
+          "lane_cascade": dict(smem_bins=128, tile_width=1),
+          "lane_cascade_restart": dict(smem_bins=128, tile_width=1, spill_records=2)}[mode]
     stride = 65536 if name == "huge_k" else 512
     for digest in (True, False):
         res = ctx.run(o, want=WANT, digest=digest, hist_stride=stride, **kw)
         for i in range(o.runs):
             ref = ob.run(oracle_opts(o, o.idx_begin + i), hist_cap=stride)
             assert_run_equal(res, i, ref, stride, digest=digest)
-    if mode != "hbm":
+    if mode.startswith("lane"):
+        assert res.timing.kernel_launches == 3 and res.timing.smem_bins == 128
+    elif mode != "hbm":
         assert res.timing.n_spilled > 0 and np.any(res.stop_reason & pkg.FLAG_SPILLED)
         assert res.timing.kernel_launches == 2
 
@@ -661,3 +666,23 @@ def test_cli_abc_front_end(pkg, ctx, tmp_path):
     got_acc = {int(x["idx"]) for x in acc}
     assert {i for i in want_acc ^ got_acc if clear[i - 70]} == set() and 0 < len(acc) < 300
     assert all(int(x["init_cells"]) == 1 and int(x["init_copies"]) == 1 for x in rows[:5])
+
+
+def test_lane_cascade_is_invisible_in_the_results(pkg, ctx):
+    """1-lane tiles with a 128-bin window (ten warps per SM instead of six): replicates whose copy numbers pass
+    127 continue in a 256-bin launch of the same kernel and, beyond 255, in HBM.  Same bits as one 256-bin launch."""
+    o = pkg.SimulationOptions(b0=1.0, b1=1.3, cells=20_000, runs=3000, initial={90: 1}, save_snapshots=False)
+    a = ctx.run(o, want=WANT, tile_width=1, smem_bins=128)
+    b = ctx.run(o, want=WANT, tile_width=1, smem_bins=256)
+    assert a.timing.tile_width == 1 and a.timing.smem_bins == 128 and a.timing.kernel_launches == 3
+    assert b.timing.smem_bins == 256 and b.timing.kernel_launches == 2
+    assert int((a.kmax >= 128).sum()) > 100 and int((a.kmax >= 256).sum()) > 10
+    for f in ("stop_reason", "nminus", "nplus", "n_events", "kmax", "hist", "sum_k", "n_div", "n_death"):
+        x, y = getattr(a, f), getattr(b, f)
+        if f == "stop_reason":
+            x, y = x & 0xFF, y & 0xFF
+        np.testing.assert_array_equal(x, y, err_msg=f)
+    np.testing.assert_array_equal(a.time.view(np.uint32), b.time.view(np.uint32))
+    np.testing.assert_array_equal(a.mean.view(np.uint32), b.mean.view(np.uint32))
+    for i in (0, int(np.argmax(a.kmax)), 2999):
+        assert_run_equal(a, i, ob.run(oracle_opts(o, o.idx_begin + i), hist_cap=512), 512, digest=False)
