@@ -519,7 +519,7 @@ def abc_leg(e, args, draws_total, with_cpu, with_e2e):
                       "l2": "256 MiB buffer rewritten before the pass"},
            "accepted_total": int(counts.sum()), "accepted_per_rank": counts.tolist(), "gather_ok": ok,
            "posterior_mean_b1_d0_d1": post, "stops_this_rank": stops.tolist(), "clocks": clocks,
-           "gpu_launches": tm.kernel_launches + 5, "roofline": roofline_block(leg, "C4", clocks)}
+           "gpu_launches": tm.kernel_launches + 8, "roofline": roofline_block(leg, "C4", clocks)}
 
     if with_e2e:
         # end to end through the host-buffer call: host prior draws in (16 B/draw), every draw's distances,
