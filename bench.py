@@ -274,7 +274,12 @@ def setup(args):
             ident = torch.tensor(list(m.comm_unique_id()), dtype=torch.uint8, device=e.dev)
         dist.broadcast(ident, 0)
         e.ctx.comm_init(bytes(ident.cpu().numpy().tobytes()), e.rank, e.world)
-    e.stream = torch.cuda.current_stream(e.dev).cuda_stream
+    # one explicit stream for everything that is timed (the legacy default stream is the NULL handle, which the
+    # library reads as "use the context's own stream")
+    e.tstream = torch.cuda.Stream(e.dev)
+    torch.cuda.set_stream(e.tstream)
+    e.stream = e.tstream.cuda_stream
+    assert e.stream != 0
     e.flush = torch.empty(256 << 20, dtype=torch.uint8, device=e.dev)  # > 126 MB L2
     e.state_mode = {"auto": m.STATE_AUTO, "smem": m.STATE_SMEM, "hbm": m.STATE_HBM}[args.state]
     return e
@@ -472,19 +477,28 @@ def abc_leg(e, args, draws_total, with_cpu, with_e2e):
     kwr = dict(rates_per_run=rates_d, abc_target=tgt_d, abc_thresholds=ABC_THRESHOLDS, hist_stride=ABC_BINS,
                tile_width=args.tile_width, slice_events=args.slice_events)
 
+    marks = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+
     def one_pass(count, shift):
         # priors -> simulation + fused epilogue -> pack -> all-gather; all enqueued on one stream
         e.flush.zero_()
+        marks[0].record()
         ctx.abc_draw_priors_device(26, idx0 + shift, count, rates_d.data_ptr(), stream=e.stream)
+        marks[1].record()
         ctx.run_device(opts, count, idx0 + shift, rs, stream=e.stream, **kwr)
+        marks[2].record()
         ctx.abc_pack(rs, rates_d.data_ptr(), (opts.b0, opts.b1, opts.d0, opts.d1), idx0 + shift, count, ABC_BINS,
                      ABC_BINS, cap, rec_d.data_ptr(), cnt_d.data_ptr(), stream=e.stream)
+        marks[3].record()
         if e.world > 1:
             ctx.abc_allgather(rec_d.data_ptr(), cnt_d.data_ptr(), ABC_BINS, cap, all_rec_d.data_ptr(),
                               all_cnt_d.data_ptr(), stream=e.stream)
+        marks[4].record()
 
-    for w in range(3):  # warm-up: three reduced passes (kernels, library buffers, the communicator)
-        one_pass(min(n, 32768), 500_000_000 + w * 1_000_000)
+    # warm-up: one pass at full size (every library buffer reaches its final size: no allocation in the timed
+    # pass), two reduced ones (kernels, the communicator)
+    for w in range(3):
+        one_pass(n if w == 0 else min(n, 32768), 500_000_000 + w * 2_000_000)
     barrier(e)
     sampler = ClockSampler(e.local_rank)
     sampler.start()
@@ -497,6 +511,9 @@ def abc_leg(e, args, draws_total, with_cpu, with_e2e):
     ms = e0.elapsed_time(e1)
     clocks = sampler.stop()
     tm = ctx.timing()
+    phases = {"priors_ms": marks[0].elapsed_time(marks[1]), "simulate_ms": marks[1].elapsed_time(marks[2]),
+              "ssa_kernel_ms": tm.kernel_ms, "pack_ms": marks[2].elapsed_time(marks[3]),
+              "allgather_ms": marks[3].elapsed_time(marks[4])}
     ms_all, events_all = reduce_max_sum(e, ms, tm.total_events)
     counts = all_cnt_d.cpu().numpy().astype(np.int64)
     merged = m.merge_gathered(all_rec_d.cpu().numpy().view(np.uint32), counts, cap, ABC_BINS)
@@ -517,6 +534,7 @@ def abc_leg(e, args, draws_total, with_cpu, with_e2e):
                       "exchange": "ecdna_b200_abc_pack + ecdna_b200_abc_allgather (NCCL, 2 collectives in one group)"
                                   if e.world > 1 else "ecdna_b200_abc_pack (one rank: nothing to exchange)",
                       "l2": "256 MiB buffer rewritten before the pass"},
+           "phases_this_rank": phases,
            "accepted_total": int(counts.sum()), "accepted_per_rank": counts.tolist(), "gather_ok": ok,
            "posterior_mean_b1_d0_d1": post, "stops_this_rank": stops.tolist(), "clocks": clocks,
            "gpu_launches": tm.kernel_launches + 8, "roofline": roofline_block(leg, "C4", clocks)}

@@ -14,8 +14,14 @@ for draws in [int(x) for x in os.environ.get("DRAWS", "125000,1000000").split(",
         p = ctx.make_params(opts, draws, rates_per_run=rates)
         p.flags |= 2 if keep else 0
         import ctypes as C
+        import time
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
         ctx._check(m.lib().ecdna_b200_run_device(ctx._h, C.byref(p), opts.idx_begin, draws, C.byref(rs), None))
+        t1 = time.perf_counter()
         tm = ctx.timing()
+        t2 = time.perf_counter()
+        print(f"  host: enqueue {1e3*(t1-t0):.1f} ms, until done {1e3*(t2-t0):.1f} ms")
         ev = t["n_events"].cpu().numpy()
         print(f"draws={draws} keep_order={keep} kernel_ms={tm.kernel_ms:.1f} events={tm.total_events:.4g} ev/s={tm.total_events/tm.kernel_ms*1e3:.4g} "
               f"max_events={int(ev.max())} p99={int(np.percentile(ev,99))} median={int(np.median(ev))}")
