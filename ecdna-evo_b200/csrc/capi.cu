@@ -374,6 +374,9 @@ int run_common(ecdna_b200_ctx* ctx, const ecdna_b200_params_t* p, uint64_t idx_b
     a.park_cap = (uint32_t)cap;
   }
 
+  a.pure_birth_binomial = (!a.rates_per_run && p->d0 == 0.f && p->d1 == 0.f && p->segregation == ECDNA_B200_SEG_BINOMIAL &&
+                           !(p->flags & ECDNA_B200_WANT_DIGEST)) ? 1u : 0u;
+  a.binomial_only = (p->segregation == ECDNA_B200_SEG_BINOMIAL && !(p->flags & ECDNA_B200_WANT_DIGEST)) ? 1u : 0u;
   a.order = nullptr;
   if (a.rates_per_run && native && n_runs >= 8192 && !(p->flags & ECDNA_B200_KEEP_ORDER)) {
     const uint32_t n32 = (uint32_t)n_runs;

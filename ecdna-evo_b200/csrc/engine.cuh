@@ -182,10 +182,10 @@ inline void plan_launch(uint64_t n, int sm, int bps, int tiles_per_block, uint32
 }
 
 // one launch of ssa_kernel<L, GLOBAL, REPLAY>; returns the grid used through *grid_out
-template <int L, bool GLOBAL, bool REPLAY, int KG>
+template <int L, bool GLOBAL, bool REPLAY, int KG, int SPEC = 0>
 int launch_kernel(ecdna_b200_ctx* ctx, SsaArgs& a, cudaStream_t st, uint64_t max_items, uint32_t* grid_out,
                   uint32_t* bps_out, uint32_t slice_events) {
-  auto kern = ssa_kernel<L, GLOBAL, REPLAY, KG>;
+  auto kern = ssa_kernel<L, GLOBAL, REPLAY, KG, ECDNA_MIN_BLOCKS_L4, SPEC>;
   constexpr int BT = block_threads<L>();
   const int warps = BT / 32;
   const int tiles_per_block = BT / L;
@@ -275,8 +275,14 @@ int launch_smem_impl(ecdna_b200_ctx* ctx, SsaArgs& a, cudaStream_t st, uint32_t 
   // the walk over the shared window is unrolled for the common window sizes
   if constexpr (L == 1 && !REPLAY) {
     if (a.kcap_s == 128) return launch_kernel<L, false, REPLAY, 1>(ctx, a, st, a.n_runs, grid, bps, slice_events);
+    // the reference's default process (pure birth, binomial segregation) has its own build of the kernel
+    if (a.kcap_s == 256 && a.pure_birth_binomial) return launch_kernel<L, false, REPLAY, 2, 1>(ctx, a, st, a.n_runs, grid, bps, slice_events);
+    if (a.kcap_s == 256 && a.binomial_only) return launch_kernel<L, false, REPLAY, 2, 2>(ctx, a, st, a.n_runs, grid, bps, slice_events);
   }
   if (!REPLAY && a.kcap_s == 256) return launch_kernel<L, false, REPLAY, 2>(ctx, a, st, a.n_runs, grid, bps, slice_events);
+  if constexpr ((L == 16 || L == 32) && !REPLAY) {  // (the tiles of small batches: C1, C5)
+    if (a.kcap_s == 512 && a.pure_birth_binomial) return launch_kernel<L, false, REPLAY, 4, 1>(ctx, a, st, a.n_runs, grid, bps, slice_events);
+  }
   if (!REPLAY && a.kcap_s == 512) return launch_kernel<L, false, REPLAY, 4>(ctx, a, st, a.n_runs, grid, bps, slice_events);
   return launch_kernel<L, false, REPLAY, 0>(ctx, a, st, a.n_runs, grid, bps, slice_events);
 }
