@@ -394,23 +394,39 @@ def ssa_leg(e, args, workload, reps, steps, warmup, idx_base, check=0, sample_cl
     return out
 
 
+def pinned_alloc(torch):
+    """Result columns in page-locked host memory (the caller owns its buffers; a pinned one copies at full speed)."""
+    tmap = {np.uint32: torch.int32, np.uint64: torch.int64, np.float32: torch.float32, np.uint8: torch.uint8}
+    keep = []
+
+    def alloc(shape, dtype):
+        t = torch.zeros(shape, dtype=tmap[dtype], pin_memory=True)
+        keep.append(t)
+        return t.numpy().view(dtype)
+    alloc.keep = keep
+    return alloc
+
+
 def e2e_ssa(e, leg, steps, idx_base):
     """End to end through the host-buffer C ABI call (what a reference-side FFI caller sees): host buffers in
-    and out, host<->device copies inside the timed region, every step."""
+    and out (page-locked, reused from step to step), host<->device copies inside the timed region, every step."""
     ctx = e.ctx
-    ctx.run(leg.opts, n_runs=leg.reps, idx_begin=idx_base, want=leg.want, **leg.knobs)  # buffers, page faults
+    alloc = pinned_alloc(e.torch)
+    host = e.m.Results(leg.reps, 0, leg.knobs.get("dyn_points", 0), leg.knobs["hist_stride"], leg.want, alloc=alloc)
+    ctx.run(leg.opts, n_runs=leg.reps, idx_begin=idx_base, want=leg.want, results=host, **leg.knobs)  # library buffers
     barrier(e)
     t0 = time.perf_counter()
     ev2 = h2d = d2h = 0
     for i in range(steps):
-        r = ctx.run(leg.opts, n_runs=leg.reps, idx_begin=idx_base + (i + 1) * 10_000_000, want=leg.want, **leg.knobs)
+        r = ctx.run(leg.opts, n_runs=leg.reps, idx_begin=idx_base + (i + 1) * 10_000_000, want=leg.want, results=host,
+                    **leg.knobs)
         ev2 += int(r.n_events.sum())  # host read of the step's result
         h2d, d2h = r.timing.h2d_bytes, r.timing.d2h_bytes
     barrier(e)
     dt = time.perf_counter() - t0
     dt_all, n_all = reduce_max_sum(e, dt, ev2)
     return {"value": n_all / dt_all, "unit": "events/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-            "steps": steps, "api": "ecdna_b200_run (host buffers; copies inside the timed region)"}
+            "steps": steps, "api": "ecdna_b200_run (page-locked host buffers; copies inside the timed region)"}
 
 
 def roofline_block(leg, workload, clocks):
@@ -544,18 +560,22 @@ def abc_leg(e, args, draws_total, with_cpu, with_e2e):
         # accept flag and summary out ("save all, filter later", abc.md:57-71), copies inside the timed region
         rates_h = ctx.abc_draw_priors(seed=26, idx_begin=idx0 + 700_000_000, n_runs=n)
         hw = ("stop_reason", "n_events", "nminus", "nplus", "abc_distance", "abc_accept", "mean", "frequency", "entropy")
-        kwh = dict(kwr, rates_per_run=rates_h, abc_target=tgt)
-        ctx.run(opts, n_runs=min(n, 32768), idx_begin=idx0 + 600_000_000, want=hw, **dict(kwh, rates_per_run=rates_h[:min(n, 32768)]))
+        alloc = pinned_alloc(torch)
+        host = m.Results(n, 0, 0, ABC_BINS, hw, alloc=alloc)
+        rates_p = alloc(rates_h.shape, np.float32)
+        rates_p[:] = rates_h
+        kwh = dict(kwr, rates_per_run=rates_p, abc_target=tgt)
+        ctx.run(opts, n_runs=n, idx_begin=idx0 + 600_000_000, want=hw, results=host, **kwh)  # library buffers at full size
         barrier(e)
         t0 = time.perf_counter()
-        r = ctx.run(opts, n_runs=n, idx_begin=idx0 + 700_000_000, want=hw, **kwh)
+        r = ctx.run(opts, n_runs=n, idx_begin=idx0 + 700_000_000, want=hw, results=host, **kwh)
         n_acc = int(r.abc_accept.sum())  # host read of the step's result
         barrier(e)
         dt = time.perf_counter() - t0
         dt_all, _ = reduce_max_sum(e, dt, n)
         out["e2e"] = {"value": draws_total / dt_all, "unit": "sims/s", "h2d_bytes_per_step": int(r.timing.h2d_bytes),
                       "d2h_bytes_per_step": int(r.timing.d2h_bytes), "steps": 1, "accepted_this_rank": n_acc,
-                      "api": "ecdna_b200_run (host prior draws in, per-draw distances/accept/summary out)"}
+                      "api": "ecdna_b200_run (page-locked host buffers: prior draws in, per-draw distances/accept/summary out)"}
     if with_cpu and e.rank == 0 and e.world == 1:
         c = cpu_port("C4", args.cpu_seconds)
         out["cpu_baseline"] = {"value": c["sims_per_sec"], "unit": "sims/s", "cores": c["cores"], "kind": "port",

@@ -353,13 +353,15 @@ class Context:
         return p
 
     def run(self, opts, n_runs=None, idx_begin=None, want=("stop_reason", "nminus", "nplus", "time", "n_events",
-                                                           "kmax", "hist"), **kw):
-        """ecdna_b200_run: host buffers in and out (what a reference-side FFI caller does)."""
+                                                           "kmax", "hist"), results=None, **kw):
+        """ecdna_b200_run: host buffers in and out (what a reference-side FFI caller does).  `results`: a
+        Results object to reuse (e.g. one whose arrays live in pinned host memory)."""
         n_runs = opts.runs if n_runs is None else n_runs
         idx_begin = opts.idx_begin if idx_begin is None else idx_begin
         p = self.make_params(opts, n_runs, **kw)
         stride = p.hist_stride or 512
-        res = Results(n_runs, p.n_snapshots, p.dyn_points, stride, want, p.n_subsamples)
+        res = results if results is not None else Results(n_runs, p.n_snapshots, p.dyn_points, stride, want, p.n_subsamples)
+        assert res.n_runs == n_runs
         self._check(lib().ecdna_b200_run(self._h, C.byref(p), idx_begin, n_runs, C.byref(res.struct)))
         res.timing = self.timing()
         return res
@@ -471,16 +473,19 @@ def _addr(a):
 class Results:
     """Caller-owned host buffers for ecdna_b200_results_t."""
 
-    def __init__(self, n_runs, n_snapshots, dyn_points, hist_stride, want, n_subsamples=0):
+    def __init__(self, n_runs, n_snapshots, dyn_points, hist_stride, want, n_subsamples=0, alloc=None):
+        """alloc(shape, dtype) -> ndarray: where the columns live (default: np.zeros; bench.py passes an allocator
+        of page-locked memory)."""
         self.struct = ResultsT()
         self.n_runs = n_runs
+        alloc = alloc or (lambda shape, dtype: np.zeros(shape, dtype=dtype))
         for name, dtype, shape in RESULT_FIELDS:
             if name not in want:
                 continue
             tail = shape(n_snapshots, dyn_points, hist_stride, n_subsamples)
             if any(t == 0 for t in tail):
                 continue
-            arr = np.zeros((n_runs,) + tail, dtype=dtype)
+            arr = alloc((n_runs,) + tail, dtype)
             setattr(self, name, arr)
             setattr(self.struct, name, arr.ctypes.data)
 
