@@ -11,6 +11,7 @@
 #include <nccl.h>  // types and prototypes only; the functions are resolved at run time
 
 #include <cstring>
+#include <mutex>
 #include <string>
 
 #include "engine.cuh"
@@ -31,9 +32,7 @@ struct NcclApi {
   std::string err;
 };
 
-NcclApi* nccl_api() {
-  static NcclApi api;
-  if (api.handle || !api.err.empty()) return &api;
+void nccl_load(NcclApi& api) {
   // a copy already loaded into the process (torch ships one) wins over the system library
   const char* names[] = {"libnccl.so.2", "libnccl.so"};
   for (const char* n : names) {
@@ -46,7 +45,7 @@ NcclApi* nccl_api() {
   }
   if (!api.handle) {
     api.err = std::string("libnccl.so.2 not found: ") + dlerror();
-    return &api;
+    return;
   }
 #define LOAD(field, sym)                                                    \
   api.field = reinterpret_cast<decltype(api.field)>(dlsym(api.handle, sym)); \
@@ -59,6 +58,12 @@ NcclApi* nccl_api() {
   LOAD(GroupEnd, "ncclGroupEnd")
   LOAD(GetErrorString, "ncclGetErrorString")
 #undef LOAD
+}
+
+NcclApi* nccl_api() {  // (loaded once, whichever thread asks first)
+  static NcclApi api;
+  static std::once_flag once;
+  std::call_once(once, [] { nccl_load(api); });
   return &api;
 }
 

@@ -11,7 +11,8 @@ for draws in [int(x) for x in os.environ.get("DRAWS", "125000,1000000").split(",
     rates = torch.from_numpy(ctx.abc_draw_priors(seed=26, idx_begin=opts.idx_begin, n_runs=draws)).to(dev)
     rs, t = m.device_results(torch, draws, ("stop_reason", "n_events"), device=dev)
     for keep in (0, 1, 0, 1):
-        p = ctx.make_params(opts, draws, rates_per_run=rates)
+        p = ctx.make_params(opts, draws, rates_per_run=rates, smem_bins=int(os.environ.get("BINS", "0")),
+                            tile_width=int(os.environ.get("TILE", "0")))
         p.flags |= 2 if keep else 0
         import ctypes as C
         import time
