@@ -134,3 +134,40 @@ def test_native_matches_reference_layout_at_size(pkg, ctx, name):
     z = np.abs(fg.mean(axis=0) - fr.mean(axis=0)) / se
     busy = (fg.mean(axis=0) + fr.mean(axis=0)) > 1e-3
     assert (z[busy] > 3.5).sum() <= 1 and z[busy].max() < 5.0
+
+
+def test_native_stream_exact_moments_at_1e6_replicates(pkg, ctx):
+    """Known answers of the process itself (no crate semantics involved), at a statistical power only the GPU
+    affords: 10^6 replicates each.
+      * Yule process (pure birth, rate b per cell) from 1 to N cells: the clock at the stop is a sum of independent
+        Exp(i b) waiting times, E[T] = sum 1/(i b), Var[T] = sum 1/(i b)^2  -> the direct method's waiting times;
+      * neutral growth: the mean copy number over all cells is a martingale, E = the initial mean (1.0)
+        -> the cell pick and the Binomial(2k, 1/2) split;
+      * linear birth-death from one cell with b = 1, d = 1/2: P(extinction before N cells) =
+        (q - q^N) / (1 - q^N), q = d / b -> the choice of the reaction."""
+    n = 1_000_000
+    # Yule: only ecDNA- cells (no segregation involved): initial {0: 1}
+    N, b = 300, 1.5
+    o = pkg.SimulationOptions(b0=b, b1=1.0, runs=n, initial={0: 1}, years=10_000, save_snapshots=False)  # (no time stop)
+    o.max_cells = N
+    r = ctx.run(o, want=("stop_reason", "time", "n_events", "nminus"))
+    assert np.all(r.stop == pkg.STOP_MAX_CELLS) and np.all(r.n_events == N - 1)
+    i = np.arange(1, N, dtype=np.float64)
+    mu, var = (1 / (i * b)).sum(), (1 / (i * b) ** 2).sum()
+    t = r.time.astype(np.float64)
+    assert abs(t.mean() - mu) < 5 * np.sqrt(var / n), (t.mean(), mu)
+    assert abs(t.var() - var) < 6 * var * np.sqrt(2.5 / n), (t.var(), var)  # (kurtosis of a sum of exponentials < 9)
+    # neutral martingale
+    o = pkg.SimulationOptions(b0=1.0, b1=1.0, cells=400, runs=n, save_snapshots=False)
+    r = ctx.run(o, want=("stop_reason", "mean", "nplus"))
+    m = r.mean.astype(np.float64)
+    assert abs(m.mean() - 1.0) < 5 * m.std() / np.sqrt(n), (m.mean(), m.std())
+    # extinction probability of a linear birth-death process from one cell
+    N, q = 60, 0.5
+    o = pkg.SimulationOptions(b0=1.0, b1=1.0, d0=q, d1=q, runs=n, initial={0: 1}, years=10_000, save_snapshots=False)
+    o.max_cells = N
+    r = ctx.run(o, want=("stop_reason",))
+    p_ext = (q - q ** N) / (1 - q ** N)
+    got = float((r.stop == pkg.STOP_NO_INDIVIDUALS).mean())
+    assert set(np.unique(r.stop)) <= {pkg.STOP_NO_INDIVIDUALS, pkg.STOP_MAX_CELLS}
+    assert abs(got - p_ext) < 5 * np.sqrt(p_ext * (1 - p_ext) / n), (got, p_ext)
