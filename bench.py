@@ -300,6 +300,16 @@ def reduce_max_sum(e, ms, count):
     return float(t.item()), float(c.item())
 
 
+def gather_floats(e, x):
+    """One float per rank, on every rank (diagnostics: which rank set the max)."""
+    t = e.torch.tensor([float(x)], dtype=e.torch.float64, device=e.dev)
+    if e.world == 1:
+        return [float(x)]
+    parts = [e.torch.zeros_like(t) for _ in range(e.world)]
+    e.dist.all_gather(parts, t)
+    return [float(p.item()) for p in parts]
+
+
 def oracle_check(e, opts, tensors, idx0, picks, dyn=None):
     """Replicates of the batch that was just timed against the CPU oracle (the specification of the native
     stream), bit for bit: stop reason, counts, events, f32 clock bits, final distribution.  Outside the timed
@@ -376,6 +386,8 @@ def ssa_leg(e, args, workload, reps, steps, warmup, idx_base, check=0, sample_cl
     out.clocks = sampler.stop() if sampler else None
     out.last = e.ctx.timing()
     out.ms_all, out.events_all = reduce_max_sum(e, ms, events)
+    out.ms_per_rank = gather_floats(e, ms / steps)
+    out.kernel_ms_per_rank = gather_floats(e, float(np.mean(kernel_ms)))
     out.value = out.events_all / (out.ms_all * 1e-3)
     out.events, out.alg_bytes, out.kernel_ms, out.steps = events, alg_bytes, float(np.mean(kernel_ms)), steps
     out.opts, out.knobs, out.want, out.desc, out.reps = opts, knobs, want, desc, reps
@@ -656,7 +668,8 @@ def main():
                        "events_per_step": leg.events_all / args.steps, "tile_width": last.tile_width,
                        "smem_bins": last.smem_bins, "state": args.state, "grid_blocks": last.grid_blocks,
                        "block_threads": last.block_threads, "blocks_per_sm": last.blocks_per_sm, "kmax": leg.kmax,
-                       "spilled": last.n_spilled,
+                       "spilled": last.n_spilled, "ms_per_step_per_rank": leg.ms_per_rank,
+                       "kernel_ms_per_rank": leg.kernel_ms_per_rank,
                        "l2": "256 MiB buffer rewritten before every step; each step simulates fresh replicate "
                              "indices", "results_ok": leg.results},
             "e2e": e2e, "gpu_launches": args.steps * last.kernel_launches, "clocks": leg.clocks, "roofline": roofline,
