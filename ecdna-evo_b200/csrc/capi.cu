@@ -378,7 +378,8 @@ int run_common(ecdna_b200_ctx* ctx, const ecdna_b200_params_t* p, uint64_t idx_b
                            !(p->flags & ECDNA_B200_WANT_DIGEST)) ? 1u : 0u;
   a.binomial_only = (p->segregation == ECDNA_B200_SEG_BINOMIAL && !(p->flags & ECDNA_B200_WANT_DIGEST)) ? 1u : 0u;
   a.order = nullptr;
-  if (a.rates_per_run && native && n_runs >= 8192 && !(p->flags & ECDNA_B200_KEEP_ORDER)) {
+  // (1-lane tiles only: they never time-slice, and the timetable of a sliced launch is keyed by replicate index)
+  if (a.rates_per_run && native && L == 1 && n_runs >= 8192 && !(p->flags & ECDNA_B200_KEEP_ORDER)) {
     const uint32_t n32 = (uint32_t)n_runs;
     CU(ctx->order.ensure((size_t)n_runs * 4));
     CU(ctx->order_hist.ensure(kLptBuckets * 4));
