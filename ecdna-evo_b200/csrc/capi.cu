@@ -140,14 +140,14 @@ void target_stats(const std::vector<uint64_t>& h, float* mean, float* ent, float
   const float nf = (float)n;
   *mean = (float)s1 / nf;
   *freq = (float)(n - h[0]) / nf;
-  float e = 0.f;
+  unsigned long long eq = 0;  // (the same fixed-point entropy as the device epilogue: bit-identical)
   uint64_t cum = 0;
   for (size_t k = 0; k < h.size(); ++k) {
-    if (h[k]) { const float pk = (float)h[k] / nf; e -= pk * log2f(pk); }
+    if (h[k]) eq += entropy_term_q40((float)h[k] / nf);
     cum += h[k];
     (*cdf)[k] = (float)cum / nf;
   }
-  *ent = e;
+  *ent = entropy_from_q40(eq);
 }
 
 int validate(ecdna_b200_ctx* ctx, const ecdna_b200_params_t* p, uint64_t n_runs) {

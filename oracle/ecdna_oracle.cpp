@@ -434,6 +434,36 @@ void dense_hist(uint64_t* dst, uint32_t cap, uint64_t nminus, HistFn&& each) {
   each([&](uint32_t k, uint64_t c) { if (k < cap) dst[k] += c; });
 }
 
+// One term of the entropy, -p log2(p) for 0 < p <= 1, as a 2^-40 fixed-point integer: single IEEE f32 operations
+// in a fixed order (the polynomial of neg_log_u24 on the mantissa of p), so that the sum - an integer - does
+// not depend on the order of the terms.  The kernel's epilogue computes the same bits.
+inline uint64_t entropy_term_q40(float p) {
+  uint32_t bits; std::memcpy(&bits, &p, 4);
+  int e = (int)(bits >> 23) - 127;
+  uint32_t fb = (bits & 0x007FFFFFu) | 0x3F800000u;
+  float f; std::memcpy(&f, &fb, 4);
+  if (f > 1.41421356f) { f = f * 0.5f; e += 1; }
+  const float x = f - 1.0f;
+  const float z = x * x;
+  float y = 7.0376836292E-2f;
+  y = fmaf(y, x, -1.1514610310E-1f);
+  y = fmaf(y, x, 1.1676998740E-1f);
+  y = fmaf(y, x, -1.2420140846E-1f);
+  y = fmaf(y, x, 1.4249322787E-1f);
+  y = fmaf(y, x, -1.6668057665E-1f);
+  y = fmaf(y, x, 2.0000714765E-1f);
+  y = fmaf(y, x, -2.4999993993E-1f);
+  y = fmaf(y, x, 3.3333331174E-1f);
+  y = y * x;
+  y = y * z;
+  y = fmaf(-0.5f, z, y);
+  const float lf = x + y;
+  const float ef = (float)e;
+  const float ln_p = fmaf(ef, 0.693359375f, fmaf(ef, -2.12194440e-4f, lf));
+  const float t = (p * ln_p) * -1.44269504088896f;
+  return (uint64_t)(std::fmax(t, 0.0f) * 1099511627776.0f);
+}
+
 void stats_from_dense(const uint64_t* hist, uint32_t cap, float* mean, float* freq, float* entropy, float* variance) {
   // ecdna-lib 3.0.2 summary statistics [RECALL R8]: all cells counted, zeros included; entropy in bits
   uint64_t n = 0, s1 = 0, s2 = 0;
@@ -441,12 +471,12 @@ void stats_from_dense(const uint64_t* hist, uint32_t cap, float* mean, float* fr
   if (n == 0) { *mean = *freq = *entropy = *variance = 0.f; return; }
   const float nf = (float)n;
   const float mu = (float)s1 / nf;
-  float ent = 0.f;
+  uint64_t eq = 0;
   for (uint32_t k = 0; k < cap; ++k)
-    if (hist[k]) { const float p = (float)hist[k] / nf; ent -= p * log2f(p); }
+    if (hist[k]) eq += entropy_term_q40((float)hist[k] / nf);
   *mean = mu;
   *freq = (float)(n - hist[0]) / nf;
-  *entropy = ent;
+  *entropy = (float)eq * 9.094947017729282e-13f;  // 2^-40
   *variance = (float)s2 / nf - mu * mu;
 }
 
