@@ -95,6 +95,8 @@ def test_tile_widths_agree(pkg, ctx, name, tile_width):
         for f in ("stop_reason", "nminus", "nplus", "n_events", "kmax", "hist", "sum_k") + (("hash", "chain") if digest else ()):
             np.testing.assert_array_equal(getattr(a, f), getattr(b, f), err_msg=f)
         np.testing.assert_array_equal(a.time.view(np.uint32), b.time.view(np.uint32))
+        for f in ("mean", "frequency", "entropy", "variance"):  # (exact moments + fixed-point entropy: no order dependence)
+            np.testing.assert_array_equal(getattr(a, f).view(np.uint32), getattr(b, f).view(np.uint32), err_msg=f)
 
 
 @pytest.mark.parametrize("mode", ["hbm", "spill_resume", "spill_restart", "spill_mixed_l8", "lane_cascade", "lane_cascade_restart"])
