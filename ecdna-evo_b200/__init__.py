@@ -85,6 +85,19 @@ class ResultsT(C.Structure):
     _fields_ = [(name, C.c_void_p) for name, _, _ in RESULT_FIELDS]
 
 
+class ResultSizesT(C.Structure):
+    _fields_ = [(name, C.c_uint64) for name, _, _ in RESULT_FIELDS]
+
+
+def query_sizes(params, n_runs):
+    """ecdna_b200_query_sizes: bytes behind every result pointer for a batch (no GPU needed)."""
+    out = ResultSizesT()
+    rc = lib().ecdna_b200_query_sizes(C.byref(params), n_runs, C.byref(out))
+    if rc != 0:
+        raise EcdnaB200Error(f"ecdna_b200_query_sizes: status {rc}")
+    return {name: getattr(out, name) for name, _, _ in RESULT_FIELDS}
+
+
 class TimingT(C.Structure):
     _fields_ = [
         ("kernel_ms", C.c_float), ("total_ms", C.c_float), ("kernel_launches", C.c_uint32),
@@ -105,7 +118,7 @@ EXPORTED_SYMBOLS = [
     "ecdna_b200_plan", "ecdna_b200_abc_draw_priors_device", "ecdna_b200_abc_pack", "ecdna_b200_abc_allgather",
     "ecdna_b200_comm_unique_id", "ecdna_b200_comm_init", "ecdna_b200_comm_release",
     "ecdna_b200_multi_create", "ecdna_b200_multi_destroy", "ecdna_b200_multi_device_count",
-    "ecdna_b200_multi_last_error", "ecdna_b200_multi_run", "ecdna_b200_multi_get_timing",
+    "ecdna_b200_multi_last_error", "ecdna_b200_multi_run", "ecdna_b200_multi_get_timing", "ecdna_b200_query_sizes",
 ]
 ERR_INTERNAL, ERR_COMM = 5, 6
 COMM_ID_BYTES = 128
@@ -167,6 +180,7 @@ def lib():
         L.ecdna_b200_multi_last_error.restype = C.c_char_p
         L.ecdna_b200_multi_run.argtypes = [C.c_void_p, C.POINTER(ParamsT), C.c_uint64, C.c_uint64, C.POINTER(ResultsT)]
         L.ecdna_b200_multi_get_timing.argtypes = [C.c_void_p, C.POINTER(TimingT)]
+        L.ecdna_b200_query_sizes.argtypes = [C.POINTER(ParamsT), C.c_uint64, C.POINTER(ResultSizesT)]
         L.ecdna_b200_comm_release.argtypes = [C.c_void_p]
         L.ecdna_b200_comm_release.restype = None
         _lib = L

@@ -546,6 +546,17 @@ extern "C" {
 
 int ecdna_b200_abi_version(void) { return ECDNA_B200_ABI_VERSION; }
 
+int ecdna_b200_query_sizes(const ecdna_b200_params_t* params, uint64_t n_runs, ecdna_b200_result_sizes_t* sizes) {
+  if (!params || !sizes || params->abi_version != ECDNA_B200_ABI_VERSION || n_runs == 0 || n_runs >= 0xFFFFFFF0ull)
+    return ECDNA_B200_ERR_BAD_PARAMS;
+  static_assert(sizeof(ecdna_b200_result_sizes_t) == C_COUNT * sizeof(uint64_t), "one size per result column");
+  const uint32_t stride = params->hist_stride ? params->hist_stride : 512u;
+  uint64_t* out = reinterpret_cast<uint64_t*>(sizes);
+  for (int c = 0; c < C_COUNT; ++c) out[c] = (uint64_t)col_bytes(c, params, stride) * n_runs;
+  if (!params->abc_enabled) sizes->abc_distance = sizes->abc_accept = 0;
+  return ECDNA_B200_OK;
+}
+
 int ecdna_b200_plan(uint64_t n_runs, uint32_t tile_width, uint32_t slice_events, uint32_t sm_count, uint32_t max_blocks_per_sm,
                     uint32_t* lanes, uint32_t* blocks_per_sm, uint32_t* tiles, uint32_t* sliced) {
   if (n_runs == 0 || sm_count == 0 || max_blocks_per_sm == 0 || !lanes || !blocks_per_sm || !tiles || !sliced)

@@ -190,6 +190,15 @@ typedef struct {
   uint32_t* sub_hist;    /* [n][n_subsamples][hist_stride] the subsampled distributions, [0] = cells without ecDNA */
 } ecdna_b200_results_t;
 
+/* Bytes a caller must provide behind every pointer of ecdna_b200_results_t for a batch of n_runs replicates
+   (same member order; 0 = that output does not exist for these parameters, e.g. snap_hist without snapshots).
+   The two-call pattern of the boundary: ecdna_b200_query_sizes -> the caller allocates -> ecdna_b200_run. */
+typedef struct {
+  uint64_t stop_reason, nminus, nplus, time, n_events, kmax, mean, frequency, entropy, variance, abc_distance,
+      abc_accept, hash, chain, hist, snap_count, snap_cells, snap_time, snap_hist, dyn_count, dyn, sum_k, n_div,
+      n_death, sub_hist;
+} ecdna_b200_result_sizes_t;
+
 /* what the last run on a context measured (CUDA events on the context's stream) */
 typedef struct {
   float kernel_ms;         /* the SSA kernel alone */
@@ -213,6 +222,9 @@ int ecdna_b200_create(int device, ecdna_b200_ctx** out);
 void ecdna_b200_destroy(ecdna_b200_ctx* ctx);
 const char* ecdna_b200_last_error(const ecdna_b200_ctx* ctx);
 int ecdna_b200_abi_version(void);
+
+/* Sizes of the per-run outputs for `params` and n_runs (no GPU needed, no context). */
+int ecdna_b200_query_sizes(const ecdna_b200_params_t* params, uint64_t n_runs, ecdna_b200_result_sizes_t* sizes);
 
 /* What the library would do with a batch (no GPU needed; the same code run plans its launch with):
    lanes per replicate, blocks of 128 threads per SM, tiles (replicates resident at once) and whether

@@ -105,3 +105,20 @@ def test_launch_plan_without_a_gpu(built):
     assert built.plan(16_384) == (1, 3, 16_384, False)
     with pytest.raises(Exception):
         built.plan(100, tile_width=3)
+
+
+def test_query_sizes_matches_the_result_buffers(built):
+    """ecdna_b200_query_sizes (the two-call pattern of SURVEY 8b): the bytes it reports are exactly the buffers the
+    ctypes mirror allocates for the same parameters; no GPU, no context."""
+    o = built.SimulationOptions(b1=1.2, d0=0.1, cells=5000, runs=7, subsamples=[10, 20])
+    make = built.Context.make_params
+    p = make(None, o, 7, dyn_points=30, hist_stride=256, abc_target=__import__("numpy").ones(8, dtype="uint64"))
+    sizes = built.query_sizes(p, 7)
+    want = tuple(n for n, _, _ in built.RESULT_FIELDS)
+    res = built.Results(7, p.n_snapshots, p.dyn_points, 256, want, p.n_subsamples)
+    for name, _, _ in built.RESULT_FIELDS:
+        assert sizes[name] == getattr(res, name).nbytes, name
+    assert sizes["snap_hist"] == 7 * 11 * 256 * 4 and sizes["dyn"] == 7 * 30 * 5 * 4 and sizes["sub_hist"] == 7 * 2 * 256 * 4
+    p2 = make(None, built.SimulationOptions(runs=3, save_snapshots=False), 3)
+    s2 = built.query_sizes(p2, 3)
+    assert s2["snap_hist"] == 0 and s2["dyn"] == 0 and s2["abc_distance"] == 0 and s2["hist"] == 3 * 512 * 4
