@@ -58,3 +58,36 @@ def test_gather_accepted_world2(tmp_path):
     r1 = [i for i in range(311, 361) if i % 4 == 0]
     want = np.array([[i, 2 * i] for i in r0] + [[i, 2 * i + 1] for i in r1], dtype=np.float32)
     np.testing.assert_array_equal(a, want)
+
+
+def test_merge_and_decode_gathered_records(pkg):
+    """What ecdna_b200_abc_allgather leaves on every rank ([world][capacity] record blocks + [world] counts) merged
+    in rank order and decoded by the layout of include/ecdna_b200.h; an overflowing rank is an error, not a
+    silent truncation."""
+    import pytest
+    bins, cap, world = 8, 5, 3
+    words = pkg.record_words(bins)
+    assert words == pkg.REC_HEADER + bins == 24
+    blocks = np.zeros((world, cap, words), dtype=np.uint32)
+    counts = np.array([2, 0, 3])
+    idx = 260
+    for r in range(world):
+        for j in range(counts[r]):
+            rec = blocks[r, j]
+            rec[0], rec[1] = idx & 0xFFFFFFFF, 1  # index with a high word
+            rec[2:6] = np.array([1.0, 1.5, 0.1, 0.2], dtype=np.float32).view(np.uint32)
+            rec[6:10] = np.array([0.01 * (idx - 259), 0.02, 0.03, 0.04], dtype=np.float32).view(np.uint32)
+            rec[10:13] = np.array([3.5, 0.9, 2.25], dtype=np.float32).view(np.uint32)
+            rec[13], rec[14], rec[15] = 1000, 7, pkg.STOP_MAX_CELLS | pkg.FLAG_SPILLED
+            rec[pkg.REC_HEADER:] = np.arange(bins) + idx
+            idx += 1
+    merged = pkg.merge_gathered(blocks, counts, cap, bins)
+    assert merged.shape == (5, words)
+    d = pkg.decode_records(merged, bins)
+    assert list(d["idx"]) == [(1 << 32) | (260 + i) for i in range(5)]
+    np.testing.assert_array_equal(d["rates"][0], np.array([1.0, 1.5, 0.1, 0.2], dtype=np.float32))
+    np.testing.assert_allclose(d["distance"][:, 0], 0.01 * np.arange(1, 6), rtol=1e-6)
+    assert d["mean"][0] == np.float32(3.5) and d["entropy"][4] == np.float32(2.25) and list(d["cells"]) == [1000] * 5
+    assert np.all(d["stop"] == pkg.STOP_MAX_CELLS) and d["hist"][3][0] == 263 and d["hist"].shape == (5, bins)
+    with pytest.raises(OverflowError):
+        pkg.merge_gathered(blocks, np.array([2, 9, 3]), cap, bins)
