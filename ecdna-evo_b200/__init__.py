@@ -114,7 +114,7 @@ class TimingT(C.Structure):
 
 EXPORTED_SYMBOLS = [
     "ecdna_b200_create", "ecdna_b200_destroy", "ecdna_b200_last_error", "ecdna_b200_abi_version", "ecdna_b200_run",
-    "ecdna_b200_run_device", "ecdna_b200_get_timing", "ecdna_b200_abc_draw_priors", "ecdna_b200_compact_accepted",
+    "ecdna_b200_run_device", "ecdna_b200_get_timing", "ecdna_b200_abc_draw_priors",
     "ecdna_b200_plan", "ecdna_b200_abc_draw_priors_device", "ecdna_b200_abc_pack", "ecdna_b200_abc_allgather",
     "ecdna_b200_comm_unique_id", "ecdna_b200_comm_init", "ecdna_b200_comm_release",
     "ecdna_b200_multi_create", "ecdna_b200_multi_destroy", "ecdna_b200_multi_device_count",
@@ -160,8 +160,6 @@ def lib():
         L.ecdna_b200_abc_draw_priors.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_float,
                                                  C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float),
                                                  C.c_void_p]
-        L.ecdna_b200_compact_accepted.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p,
-                                                  C.POINTER(C.c_uint32), C.c_void_p]
         L.ecdna_b200_abc_draw_priors_device.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_float,
                                                         C.POINTER(C.c_float), C.POINTER(C.c_float),
                                                         C.POINTER(C.c_float), C.c_void_p, C.c_void_p]
@@ -428,13 +426,6 @@ class Context:
                                                    rec_bins, capacity, C.c_void_p(all_records_dev_ptr),
                                                    C.c_void_p(all_counts_dev_ptr),
                                                    C.c_void_p(stream) if stream else None))
-
-    def compact_accepted(self, accept_dev_ptr, n_runs, out_idx_dev_ptr, stream=None):
-        n = C.c_uint32(0)
-        self._check(lib().ecdna_b200_compact_accepted(self._h, C.c_void_p(accept_dev_ptr), n_runs,
-                                                      C.c_void_p(out_idx_dev_ptr), C.byref(n),
-                                                      C.c_void_p(stream) if stream else None))
-        return n.value
 
 
 class MultiContext(Context):

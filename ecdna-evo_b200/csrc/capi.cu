@@ -492,54 +492,6 @@ __global__ void prior_kernel(uint32_t seed_lo, uint32_t seed_hi, uint64_t idx_be
   out[4 * (size_t)i + 3] = __fmaf_rn(u3, hi3 - lo3, lo3);
 }
 
-constexpr int kCompactBlock = 1024;
-__global__ void compact_count(const uint8_t* flag, uint32_t n, uint32_t* block_counts) {
-  const uint32_t i = blockIdx.x * kCompactBlock + threadIdx.x;
-  const int c = __syncthreads_count(i < n && flag[i] != 0);
-  if (threadIdx.x == 0) block_counts[blockIdx.x] = (uint32_t)c;
-}
-__global__ void compact_scan(uint32_t* block_counts, uint32_t n_blocks, uint32_t* total) {
-  // single block: exclusive scan of the block counts (n_blocks is small: n_runs / 1024)
-  __shared__ uint32_t carry;
-  if (threadIdx.x == 0) carry = 0;
-  __syncthreads();
-  for (uint32_t base = 0; base < n_blocks; base += blockDim.x) {
-    const uint32_t i = base + threadIdx.x;
-    uint32_t v = i < n_blocks ? block_counts[i] : 0u;
-    const uint32_t lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
-    uint32_t inc = v;
-    for (int o = 1; o < 32; o <<= 1) { const uint32_t u = __shfl_up_sync(0xFFFFFFFFu, inc, o); if ((int)lane >= o) inc += u; }
-    __shared__ uint32_t wsum[32];
-    if (lane == 31) wsum[w] = inc;
-    __syncthreads();
-    if (w == 0) {
-      uint32_t s = lane < (blockDim.x >> 5) ? wsum[lane] : 0u;
-      uint32_t si = s;
-      for (int o = 1; o < 32; o <<= 1) { const uint32_t u = __shfl_up_sync(0xFFFFFFFFu, si, o); if ((int)lane >= o) si += u; }
-      wsum[lane] = si - s;
-    }
-    __syncthreads();
-    const uint32_t excl = carry + wsum[w] + inc - v;
-    if (i < n_blocks) block_counts[i] = excl;
-    __syncthreads();
-    if (threadIdx.x == blockDim.x - 1) carry = excl + v;
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) *total = carry;
-}
-__global__ void compact_scatter(const uint8_t* flag, uint32_t n, const uint32_t* block_offsets, uint32_t* out) {
-  const uint32_t i = blockIdx.x * kCompactBlock + threadIdx.x;
-  const bool f = i < n && flag[i] != 0;
-  const uint32_t lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
-  const uint32_t b = __ballot_sync(0xFFFFFFFFu, f);
-  __shared__ uint32_t wcount[32];
-  if (lane == 0) wcount[w] = __popc(b);
-  __syncthreads();
-  uint32_t off = block_offsets[blockIdx.x];
-  for (uint32_t j = 0; j < w; ++j) off += wcount[j];
-  if (f) out[off + __popc(b & ((1u << lane) - 1u))] = i;
-}
-
 }  // namespace
 
 extern "C" {
@@ -678,25 +630,6 @@ int ecdna_b200_abc_draw_priors_device(ecdna_b200_ctx* ctx, uint64_t seed, uint64
   prior_kernel<<<(n + 255) / 256, 256, 0, st>>>((uint32_t)seed, (uint32_t)(seed >> 32), idx_begin, n, b0, b1_range[0],
                                                 b1_range[1], d0_range[0], d0_range[1], d1_range[0], d1_range[1], rates_dev);
   CU(cudaGetLastError());
-  return ECDNA_B200_OK;
-}
-
-int ecdna_b200_compact_accepted(ecdna_b200_ctx* ctx, const uint8_t* accept_dev, uint64_t n_runs,
-                                uint32_t* accepted_idx_dev, uint32_t* n_accepted, void* cuda_stream) {
-  if (!ctx || !accept_dev || !accepted_idx_dev || !n_accepted || n_runs == 0 || n_runs >= (1ull << 32))
-    return fail(ctx, ECDNA_B200_ERR_BAD_PARAMS, "bad compaction request");
-  CU(cudaSetDevice(ctx->device));
-  cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
-  const uint32_t n = (uint32_t)n_runs;
-  const uint32_t nb = (n + kCompactBlock - 1) / kCompactBlock;
-  CU(ctx->scratch.ensure(((size_t)nb + 1) * 4));  // block counts + total
-  uint32_t* counts = (uint32_t*)ctx->scratch.p;
-  compact_count<<<nb, kCompactBlock, 0, st>>>(accept_dev, n, counts);
-  compact_scan<<<1, 1024, 0, st>>>(counts, nb, counts + nb);
-  compact_scatter<<<nb, kCompactBlock, 0, st>>>(accept_dev, n, counts, accepted_idx_dev);
-  CU(cudaGetLastError());
-  CU(cudaMemcpyAsync(n_accepted, counts + nb, 4, cudaMemcpyDeviceToHost, st));
-  CU(cudaStreamSynchronize(st));
   return ECDNA_B200_OK;
 }
 

@@ -14,7 +14,9 @@ def rank_range(idx_begin, n_runs, rank, world):
 
 
 def gather_accepted(torch, dist, payload):
-    """All-gather a [n_accepted, C] tensor whose first dimension differs per rank.
+    """All-gather a [n_accepted, C] tensor whose first dimension differs per rank, through torch.distributed: for
+    jobs whose ranks hold accepted records as tensors (e.g. a CPU post-processing step over gloo).  The GPU path of
+    the library is ecdna_b200_abc_pack + ecdna_b200_abc_allgather (csrc/abc_gather.cu), which needs no host round trip.
 
     Two collectives: the counts, then fixed-stride records padded to the largest count (NCCL has no
     all-gather-v).  Returns the concatenation in rank order."""

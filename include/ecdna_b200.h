@@ -261,11 +261,6 @@ int ecdna_b200_abc_draw_priors_device(ecdna_b200_ctx* ctx, uint64_t seed, uint64
                                       const float b1_range[2], const float d0_range[2], const float d1_range[2],
                                       float* rates_dev, void* cuda_stream);
 
-/* Compacts the accepted runs of the last ecdna_b200_run_device call: writes their indices
-   (relative to idx_begin) to `accepted_idx` (device, [n_runs]) and the count to *n_accepted (host). */
-int ecdna_b200_compact_accepted(ecdna_b200_ctx* ctx, const uint8_t* accept_dev, uint64_t n_runs,
-                                uint32_t* accepted_idx_dev, uint32_t* n_accepted, void* cuda_stream);
-
 /* ---- several GPUs of one box from one process (the reference's rayon loop, main.rs:214-225) ----
    The index range of a batch is cut into contiguous blocks, one per GPU, each driven by its own host
    thread and context; the blocks' results are written into the caller's arrays at the block's offset, so
