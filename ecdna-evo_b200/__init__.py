@@ -98,6 +98,54 @@ def query_sizes(params, n_runs):
     return {name: getattr(out, name) for name, _, _ in RESULT_FIELDS}
 
 
+class SparseT(C.Structure):
+    """ecdna_b200_sparse_t"""
+    _fields_ = [("final_dist", C.c_void_p), ("snap_dist", C.c_void_p), ("sub_dist", C.c_void_p), ("arena", C.c_void_p),
+                ("arena_words", C.c_uint64), ("arena_used", C.c_uint64)]
+
+
+# ecdna_b200_dist_t (40 bytes)
+DIST_DTYPE = np.dtype([("cells", np.uint64), ("nminus", np.uint64), ("offset", np.uint64), ("time", np.float32),
+                       ("k_len", np.uint32), ("k_min", np.uint16), ("flags", np.uint16), ("reserved", np.uint32)])
+DIST_TAKEN, DIST_TRUNCATED = 1, 2
+ERR_ARENA = 7
+
+
+class Sparse:
+    """Caller-owned buffers of the sparse return: one descriptor per distribution and the arena of occupied bins."""
+
+    def __init__(self, n_runs, n_snapshots, n_subsamples, arena_words):
+        self.struct = SparseT()
+        self.final_dist = np.zeros(n_runs, dtype=DIST_DTYPE)
+        self.snap_dist = np.zeros((n_runs, n_snapshots), dtype=DIST_DTYPE)
+        self.sub_dist = np.zeros((n_runs, n_subsamples), dtype=DIST_DTYPE)
+        self.struct.final_dist = self.final_dist.ctypes.data
+        if n_snapshots:
+            self.struct.snap_dist = self.snap_dist.ctypes.data
+        if n_subsamples:
+            self.struct.sub_dist = self.sub_dist.ctypes.data
+        self.resize(arena_words)
+
+    def resize(self, arena_words):
+        self.arena = np.zeros(max(int(arena_words), 1), dtype=np.uint32)
+        self.struct.arena = self.arena.ctypes.data
+        self.struct.arena_words = int(arena_words)
+
+    @property
+    def arena_used(self):
+        return int(self.struct.arena_used)
+
+    def dense(self, desc, stride):
+        """The dense form of the distributions `desc` (any shape): [..., stride] with [0] = cells without ecDNA."""
+        flat = desc.reshape(-1)
+        out = np.zeros((flat.size, stride), dtype=np.uint32)
+        for i, d in enumerate(flat):
+            out[i, 0] = d["nminus"]
+            n, k0, off = int(d["k_len"]), int(d["k_min"]), int(d["offset"])
+            out[i, k0:k0 + n] = self.arena[off:off + n]
+        return out.reshape(desc.shape + (stride,))
+
+
 class TimingT(C.Structure):
     _fields_ = [
         ("kernel_ms", C.c_float), ("total_ms", C.c_float), ("kernel_launches", C.c_uint32),
@@ -119,6 +167,7 @@ EXPORTED_SYMBOLS = [
     "ecdna_b200_comm_unique_id", "ecdna_b200_comm_init", "ecdna_b200_comm_release",
     "ecdna_b200_multi_create", "ecdna_b200_multi_destroy", "ecdna_b200_multi_device_count",
     "ecdna_b200_multi_last_error", "ecdna_b200_multi_run", "ecdna_b200_multi_get_timing", "ecdna_b200_query_sizes",
+    "ecdna_b200_run_sparse", "ecdna_b200_sparse_fetch", "ecdna_b200_multi_run_sparse", "ecdna_b200_multi_sparse_fetch",
 ]
 ERR_INTERNAL, ERR_COMM = 5, 6
 COMM_ID_BYTES = 128
@@ -179,6 +228,11 @@ def lib():
         L.ecdna_b200_multi_run.argtypes = [C.c_void_p, C.POINTER(ParamsT), C.c_uint64, C.c_uint64, C.POINTER(ResultsT)]
         L.ecdna_b200_multi_get_timing.argtypes = [C.c_void_p, C.POINTER(TimingT)]
         L.ecdna_b200_query_sizes.argtypes = [C.POINTER(ParamsT), C.c_uint64, C.POINTER(ResultSizesT)]
+        L.ecdna_b200_run_sparse.argtypes = [C.c_void_p, C.POINTER(ParamsT), C.c_uint64, C.c_uint64, C.POINTER(ResultsT),
+                                            C.POINTER(SparseT)]
+        L.ecdna_b200_sparse_fetch.argtypes = [C.c_void_p, C.POINTER(SparseT)]
+        L.ecdna_b200_multi_run_sparse.argtypes = L.ecdna_b200_run_sparse.argtypes
+        L.ecdna_b200_multi_sparse_fetch.argtypes = [C.c_void_p, C.POINTER(SparseT)]
         L.ecdna_b200_comm_release.argtypes = [C.c_void_p]
         L.ecdna_b200_comm_release.restype = None
         _lib = L
@@ -378,6 +432,29 @@ class Context:
         res.timing = self.timing()
         return res
 
+    _run_sparse_fn, _sparse_fetch_fn = "ecdna_b200_run_sparse", "ecdna_b200_sparse_fetch"
+
+    def run_sparse(self, opts, n_runs=None, idx_begin=None, want=("stop_reason", "nminus", "nplus", "time", "n_events",
+                                                                  "kmax"), arena_words=None, **kw):
+        """ecdna_b200_run_sparse: the distributions come back as descriptors + one arena of occupied bins
+        (res.sparse).  arena_words=None: a first guess, then ecdna_b200_sparse_fetch with the size the library
+        reports (the two-call pattern; the batch is not simulated again)."""
+        n_runs = opts.runs if n_runs is None else n_runs
+        idx_begin = opts.idx_begin if idx_begin is None else idx_begin
+        p = self.make_params(opts, n_runs, **kw)
+        res = Results(n_runs, p.n_snapshots, p.dyn_points, p.hist_stride or 512, want, p.n_subsamples)
+        sp = Sparse(n_runs, p.n_snapshots, p.n_subsamples, 0 if arena_words is None else arena_words)
+        rc = getattr(lib(), self._run_sparse_fn)(self._h, C.byref(p), idx_begin, n_runs, C.byref(res.struct), C.byref(sp.struct))
+        res.refetched = False
+        if rc == ERR_ARENA and arena_words is None:
+            sp.resize(sp.arena_used)
+            rc = getattr(lib(), self._sparse_fetch_fn)(self._h, C.byref(sp.struct))
+            res.refetched = True
+        self._check(rc)
+        res.sparse = sp
+        res.timing = self.timing()
+        return res
+
     def run_device(self, opts, n_runs, idx_begin, results_struct, stream=None, **kw):
         """ecdna_b200_run_device: outputs (and bulk inputs) are device pointers; asynchronous."""
         p = self.make_params(opts, n_runs, **kw)
@@ -448,6 +525,8 @@ class MultiContext(Context):
     def _check(self, rc):
         if rc != 0:
             raise EcdnaB200Error(f"status {rc}: {lib().ecdna_b200_multi_last_error(self._h).decode()}")
+
+    _run_sparse_fn, _sparse_fetch_fn = "ecdna_b200_multi_run_sparse", "ecdna_b200_multi_sparse_fetch"
 
     def run(self, opts, n_runs=None, idx_begin=None, want=("stop_reason", "nminus", "nplus", "time", "n_events",
                                                            "kmax", "hist"), **kw):

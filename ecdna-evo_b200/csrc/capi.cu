@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "engine.cuh"
+#include "sparse.cuh"
 #include "subsample.cuh"
 #include "uniform_replay.cuh"
 
@@ -185,7 +186,7 @@ int validate(ecdna_b200_ctx* ctx, const ecdna_b200_params_t* p, uint64_t n_runs)
 
 // device_io: results and the bulk inputs are device pointers already
 int run_common(ecdna_b200_ctx* ctx, const ecdna_b200_params_t* p, uint64_t idx_begin, uint64_t n_runs,
-               const ecdna_b200_results_t* results, cudaStream_t st, bool device_io) {
+               const ecdna_b200_results_t* results, cudaStream_t st, bool device_io, bool sparse = false) {
   int rc = validate(ctx, p, n_runs);
   if (rc) return rc;
   if (!results) return fail(ctx, ECDNA_B200_ERR_BAD_PARAMS, "results is NULL");
@@ -193,6 +194,7 @@ int run_common(ecdna_b200_ctx* ctx, const ecdna_b200_params_t* p, uint64_t idx_b
   ecdna_b200_timing_t& tm = ctx->timing;
   tm = ecdna_b200_timing_t{};
   ctx->have_total = !device_io;
+  ctx->sp.valid = false;
 
   SsaArgs a{};
   a.rate[0] = p->b0; a.rate[1] = p->b1; a.rate[2] = p->d0; a.rate[3] = p->d1;
@@ -343,7 +345,10 @@ int run_common(ecdna_b200_ctx* ctx, const ecdna_b200_params_t* p, uint64_t idx_b
     for (int c = 0; c < C_COUNT; ++c) {
       void** hs = col_slot(&host, c);
       void** ds = col_slot(&dev, c);
-      if (!*hs) continue;
+      // (the sparse return packs the distributions on the device: they exist there whether or not the host wants them)
+      const bool for_sparse = sparse && (c == C_HIST || c == C_SNAPHIST || c == C_SUBHIST || c == C_SNAPCOUNT ||
+                                         c == C_SNAPTIME || c == C_TIME || c == C_STOP);
+      if (!*hs && !for_sparse) continue;
       const size_t bytes = col_bytes(c, p, stride) * n_runs;
       if (bytes == 0) { *ds = nullptr; continue; }
       CU(ctx->cols[c].ensure(bytes));
@@ -455,6 +460,27 @@ int run_common(ecdna_b200_ctx* ctx, const ecdna_b200_params_t* p, uint64_t idx_b
     tm.kernel_launches += 1;
   }
 
+  if (sparse) {  // measure every distribution and lay the windows out (sparse.cuh)
+    SparseArgs sa{};
+    sa.n_runs = a.n_runs; sa.n_snap = a.n_snap; sa.n_sub = dev.sub_hist ? p->n_subsamples : 0u; sa.stride = stride;
+    sa.rows = (unsigned long long)n_runs * (1ull + sa.n_snap + sa.n_sub);
+    sa.hist = dev.hist; sa.snap_hist = dev.snap_hist; sa.sub_hist = dev.sub_hist;
+    sa.snap_count = dev.snap_count; sa.time = dev.time; sa.snap_time = dev.snap_time; sa.stop = dev.stop_reason;
+    const uint64_t chunks = (sa.rows + kSparseChunk - 1) / kSparseChunk;
+    CU(ctx->sp_desc.ensure((size_t)sa.rows * sizeof(ecdna_b200_dist_t)));
+    CU(ctx->sp_len.ensure((size_t)sa.rows * 4));
+    CU(ctx->sp_bsum.ensure((size_t)(chunks + 1) * 8));
+    sa.desc = (ecdna_b200_dist_t*)ctx->sp_desc.p; sa.len = (uint32_t*)ctx->sp_len.p; sa.bsum = (unsigned long long*)ctx->sp_bsum.p;
+    sparse_measure<<<(unsigned)((sa.rows + 7) / 8), 256, 0, st>>>(sa);
+    sparse_chunk_sums<<<(unsigned)chunks, 256, 0, st>>>(sa);
+    sparse_scan_chunks<<<1, 256, 0, st>>>(sa.bsum, (uint32_t)chunks);
+    sparse_offsets<<<(unsigned)chunks, 256, 0, st>>>(sa);
+    CU(cudaGetLastError());
+    tm.kernel_launches += 4;
+    ctx->sp.n_runs = n_runs; ctx->sp.n_snap = sa.n_snap; ctx->sp.n_sub = sa.n_sub; ctx->sp.rows = sa.rows; ctx->sp.stride = stride;
+    ctx->sp.packed = false;
+  }
+
   if (!device_io) {
     for (int c = 0; c < C_COUNT; ++c) {
       void** hs = col_slot(&host, c);
@@ -464,8 +490,18 @@ int run_common(ecdna_b200_ctx* ctx, const ecdna_b200_params_t* p, uint64_t idx_b
       CU(cudaMemcpyAsync(*hs, *ds, bytes, cudaMemcpyDeviceToHost, st));
       tm.d2h_bytes += bytes;
     }
+    unsigned long long sparse_words = 0;
+    if (sparse) {
+      const uint64_t chunks = (ctx->sp.rows + kSparseChunk - 1) / kSparseChunk;
+      CU(cudaMemcpyAsync(&sparse_words, (unsigned long long*)ctx->sp_bsum.p + chunks, 8, cudaMemcpyDeviceToHost, st));
+      tm.d2h_bytes += 8;
+    }
     CU(cudaEventRecord(ctx->ev_end, st));
     CU(cudaStreamSynchronize(st));
+    if (sparse) {
+      ctx->sp.words = sparse_words;
+      ctx->sp.valid = true;
+    }
     // every replicate of the batch must have gone through the epilogue (a lost one would leave zeros behind)
     unsigned long long fin = 0;
     CU(cudaMemcpy(&fin, (char*)ctx->counters.p + kTotalsOffset + 7 * 8, 8, cudaMemcpyDeviceToHost));
@@ -494,7 +530,91 @@ __global__ void prior_kernel(uint32_t seed_lo, uint32_t seed_hi, uint64_t idx_be
 
 }  // namespace
 
+namespace ecdna {
+
+int sparse_prepare(ecdna_b200_ctx* ctx, const ecdna_b200_params_t* p, uint64_t idx_begin, uint64_t n_runs,
+                   const ecdna_b200_results_t* results, uint64_t* words) {
+  static const ecdna_b200_results_t none{};
+  const int rc = run_common(ctx, p, idx_begin, n_runs, results ? results : &none, ctx->stream, false, true);
+  if (rc) return rc;
+  *words = ctx->sp.words;
+  return ECDNA_B200_OK;
+}
+
+int sparse_fetch(ecdna_b200_ctx* ctx, ecdna_b200_dist_t* final_dist, ecdna_b200_dist_t* snap_dist,
+                 ecdna_b200_dist_t* sub_dist, uint32_t* arena, uint64_t base) {
+  if (!ctx->sp.valid) return fail(ctx, ECDNA_B200_ERR_BAD_PARAMS, "no sparse batch on the device: call ecdna_b200_run_sparse first");
+  CU(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  const auto& sp = ctx->sp;
+  if (arena && sp.words && !sp.packed) {
+    SparseArgs sa{};
+    sa.n_runs = (uint32_t)sp.n_runs; sa.n_snap = (uint32_t)sp.n_snap; sa.n_sub = (uint32_t)sp.n_sub; sa.stride = sp.stride;
+    sa.rows = sp.rows;
+    sa.hist = (const uint32_t*)ctx->cols[C_HIST].p; sa.snap_hist = (const uint32_t*)ctx->cols[C_SNAPHIST].p;
+    sa.sub_hist = (const uint32_t*)ctx->cols[C_SUBHIST].p;
+    sa.snap_count = (const uint32_t*)ctx->cols[C_SNAPCOUNT].p; sa.time = (const float*)ctx->cols[C_TIME].p;
+    sa.snap_time = (const float*)ctx->cols[C_SNAPTIME].p; sa.stop = (const uint32_t*)ctx->cols[C_STOP].p;
+    sa.desc = (ecdna_b200_dist_t*)ctx->sp_desc.p; sa.len = (uint32_t*)ctx->sp_len.p; sa.bsum = (unsigned long long*)ctx->sp_bsum.p;
+    CU(ctx->sp_arena.ensure((size_t)sp.words * 4));
+    sa.arena = (uint32_t*)ctx->sp_arena.p;
+    sparse_pack<<<(unsigned)((sa.rows + 7) / 8), 256, 0, st>>>(sa);
+    CU(cudaGetLastError());
+    ctx->timing.kernel_launches += 1;
+    ctx->sp.packed = true;
+  }
+  const ecdna_b200_dist_t* d = (const ecdna_b200_dist_t*)ctx->sp_desc.p;
+  const size_t ds = sizeof(ecdna_b200_dist_t);
+  if (final_dist) { CU(cudaMemcpyAsync(final_dist, d, sp.n_runs * ds, cudaMemcpyDeviceToHost, st)); ctx->timing.d2h_bytes += sp.n_runs * ds; }
+  if (snap_dist && sp.n_snap) {
+    CU(cudaMemcpyAsync(snap_dist, d + sp.n_runs, sp.n_runs * sp.n_snap * ds, cudaMemcpyDeviceToHost, st));
+    ctx->timing.d2h_bytes += sp.n_runs * sp.n_snap * ds;
+  }
+  if (sub_dist && sp.n_sub) {
+    CU(cudaMemcpyAsync(sub_dist, d + sp.n_runs * (1 + sp.n_snap), sp.n_runs * sp.n_sub * ds, cudaMemcpyDeviceToHost, st));
+    ctx->timing.d2h_bytes += sp.n_runs * sp.n_sub * ds;
+  }
+  if (arena && sp.words) {
+    CU(cudaMemcpyAsync(arena + base, ctx->sp_arena.p, (size_t)sp.words * 4, cudaMemcpyDeviceToHost, st));
+    ctx->timing.d2h_bytes += sp.words * 4;
+  }
+  CU(cudaEventRecord(ctx->ev_end, st));
+  CU(cudaStreamSynchronize(st));
+  if (base) {
+    if (final_dist) for (uint64_t i = 0; i < sp.n_runs; ++i) final_dist[i].offset += base;
+    if (snap_dist) for (uint64_t i = 0; i < sp.n_runs * sp.n_snap; ++i) snap_dist[i].offset += base;
+    if (sub_dist) for (uint64_t i = 0; i < sp.n_runs * sp.n_sub; ++i) sub_dist[i].offset += base;
+  }
+  return ECDNA_B200_OK;
+}
+
+}  // namespace ecdna
+
 extern "C" {
+
+int ecdna_b200_run_sparse(ecdna_b200_ctx* ctx, const ecdna_b200_params_t* params, uint64_t idx_begin, uint64_t n_runs,
+                          const ecdna_b200_results_t* results, ecdna_b200_sparse_t* sparse) {
+  if (!ctx) return ECDNA_B200_ERR_BAD_PARAMS;
+  if (!sparse) return fail(ctx, ECDNA_B200_ERR_BAD_PARAMS, "sparse is NULL");
+  uint64_t words = 0;
+  const int rc = sparse_prepare(ctx, params, idx_begin, n_runs, results, &words);
+  if (rc) return rc;
+  return ecdna_b200_sparse_fetch(ctx, sparse);
+}
+
+int ecdna_b200_sparse_fetch(ecdna_b200_ctx* ctx, ecdna_b200_sparse_t* sparse) {
+  if (!ctx) return ECDNA_B200_ERR_BAD_PARAMS;
+  if (!sparse) return fail(ctx, ECDNA_B200_ERR_BAD_PARAMS, "sparse is NULL");
+  if (!ctx->sp.valid) return fail(ctx, ECDNA_B200_ERR_BAD_PARAMS, "no sparse batch on the device: call ecdna_b200_run_sparse first");
+  sparse->arena_used = ctx->sp.words;
+  const bool fits = ctx->sp.words == 0 || (sparse->arena && sparse->arena_words >= ctx->sp.words);
+  const int rc = sparse_fetch(ctx, sparse->final_dist, sparse->snap_dist, sparse->sub_dist, fits ? sparse->arena : nullptr, 0);
+  if (rc) return rc;
+  if (!fits)
+    return fail(ctx, ECDNA_B200_ERR_ARENA, "the batch needs an arena of " + std::to_string(ctx->sp.words) + " words, the caller gave " +
+                                               std::to_string(sparse->arena ? sparse->arena_words : 0));
+  return ECDNA_B200_OK;
+}
 
 int ecdna_b200_abi_version(void) { return ECDNA_B200_ABI_VERSION; }
 
@@ -558,7 +678,8 @@ void ecdna_b200_destroy(ecdna_b200_ctx* ctx) {
   ecdna_b200_comm_release(ctx);
   DevBuf* bufs[] = {&ctx->init_k, &ctx->init_c, &ctx->snap, &ctx->rates, &ctx->replay, &ctx->replay_off,
                     &ctx->abc_cdf, &ctx->arena, &ctx->counters, &ctx->scratch, &ctx->park_list, &ctx->park_rec, &ctx->park_list2, &ctx->park_rec2, &ctx->order, &ctx->order_hist, &ctx->ts_ring, &ctx->ts_rec, &ctx->sub_sizes, &ctx->hist_tmp,
-                    &ctx->cells, &ctx->zig, &ctx->pack_idx, &ctx->pack_out, &ctx->pack_cnt};
+                    &ctx->cells, &ctx->zig, &ctx->pack_idx, &ctx->pack_out, &ctx->pack_cnt, &ctx->sp_desc, &ctx->sp_len,
+                    &ctx->sp_bsum, &ctx->sp_arena};
   for (DevBuf* b : bufs) b->release();
   for (auto& b : ctx->cols) b.release();
   cudaEventDestroy(ctx->ev_begin); cudaEventDestroy(ctx->ev_k0); cudaEventDestroy(ctx->ev_k1); cudaEventDestroy(ctx->ev_end);

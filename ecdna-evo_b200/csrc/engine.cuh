@@ -59,7 +59,13 @@ struct ecdna_b200_ctx {
   std::string err;
   ecdna::DevBuf init_k, init_c, snap, rates, replay, replay_off, abc_cdf, arena, counters, scratch, park_list, park_rec,
       park_list2, park_rec2, order, order_hist, cells, zig, ts_ring, ts_rec, sub_sizes, hist_tmp, pack_idx, pack_out, pack_cnt,
-      cols[ecdna::C_COUNT];
+      sp_desc, sp_len, sp_bsum, sp_arena, cols[ecdna::C_COUNT];
+  // the packed batch the last ecdna_b200_run_sparse left on the device (sparse.cuh)
+  struct {
+    bool valid = false, packed = false;
+    uint64_t n_runs = 0, n_snap = 0, n_sub = 0, rows = 0, words = 0;
+    uint32_t stride = 0;
+  } sp;
   size_t arena_words = 0, arena_kcap = 0;
   ecdna_b200_timing_t timing{};
 };
@@ -259,6 +265,14 @@ int launch_kernel(ecdna_b200_ctx* ctx, SsaArgs& a, cudaStream_t st, uint64_t max
   *bps_out = (uint32_t)bps;
   return ECDNA_B200_OK;
 }
+
+// sparse return (capi.cu): the batch is simulated, measured and laid out on the device (*words = arena words it
+// needs); sparse_fetch packs it and copies descriptors and arena to the host, the arena at word `base` of the
+// caller's arena and the offsets shifted by `base` (blocks of a multi-GPU batch follow each other)
+int sparse_prepare(ecdna_b200_ctx* ctx, const ecdna_b200_params_t* p, uint64_t idx_begin, uint64_t n_runs,
+                   const ecdna_b200_results_t* results, uint64_t* words);
+int sparse_fetch(ecdna_b200_ctx* ctx, ecdna_b200_dist_t* final_dist, ecdna_b200_dist_t* snap_dist,
+                 ecdna_b200_dist_t* sub_dist, uint32_t* arena, uint64_t base);
 
 // the launch with the histogram in the HBM arena (ssa_hbm.cu): every replicate of the batch, or, when
 // a.park_list is set, the replicates the shared-memory launch parked

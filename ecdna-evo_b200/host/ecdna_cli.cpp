@@ -6,7 +6,8 @@
 // (src/process.rs:31-55) with the names of src/lib.rs:27-45: one JSON histogram per triggered
 // snapshot, one for the final state, one per --subsamples size.
 //
-// The index range runs on every visible B200 (ecdna_b200_multi_run: one host thread and context per GPU),
+// The index range runs on every visible B200 (ecdna_b200_multi_run_sparse: one host thread and context per GPU; the
+// distributions come back as descriptors + occupied bins, a tenth of the dense form for the default snapshots),
 // in chunks, so that host memory is O(chunk) whatever --runs is; the files of a chunk are written while the
 // next one is simulated.  `ecdna abc --target FILE.json ...` is the front end of the reference's removed ABC
 // binary (abc.md:10-55): prior draws over (b1, d0, d1), one run per draw, abc.csv with every draw.
@@ -250,10 +251,11 @@ void mkdirs(const std::string& path) {
   }
 }
 
-// process.rs:31-55
-void save(const Cli& c, const std::string& filename, float time, const uint32_t* hist, uint32_t len, int verbosity) {
-  uint64_t cells = 0;
-  for (uint32_t k = 0; k < len; ++k) cells += hist[k];
+// process.rs:31-55; the distribution arrives as the library's sparse form: cells without ecDNA in the descriptor,
+// the occupied copy numbers k_min .. k_min + k_len - 1 in the arena
+void save(const Cli& c, const std::string& filename, const ecdna_b200_dist_t& d, const uint32_t* arena, int verbosity) {
+  const uint64_t cells = d.cells;
+  const float time = d.time;
   char tbuf[64];
   std::snprintf(tbuf, sizeof tbuf, "%.1f", (double)time);
   std::string tp;
@@ -267,10 +269,12 @@ void save(const Cli& c, const std::string& filename, float time, const uint32_t*
   if (!f) { std::fprintf(stderr, "Cannot create %s\n", file.c_str()); std::exit(101); }
   f << "{";
   bool first = true;
-  for (uint32_t k = 0; k < len; ++k) {
-    if (!hist[k]) continue;
+  if (d.nminus) { f << "\"0\":" << d.nminus; first = false; }
+  const uint32_t* bins = arena + d.offset;
+  for (uint32_t i = 0; i < d.k_len; ++i) {
+    if (!bins[i]) continue;
     if (!first) f << ",";
-    f << "\"" << k << "\":" << hist[k];
+    f << "\"" << (d.k_min + i) << "\":" << bins[i];
     first = false;
   }
   f << "}";
@@ -468,39 +472,46 @@ int main(int argc, char** argv) {
 
   // The index range goes through the library in chunks (host memory is O(chunk), whatever --runs is); the
   // files of a chunk are written while the next chunk is simulated.
-  uint32_t stride = 1024;
+  uint32_t stride = 1024;  // bins per distribution ON THE DEVICE; the host receives the occupied windows only
   const size_t n_snap = snapshots.size();
-  auto per_replicate_bytes = [&](uint32_t st) { return (size_t)(1 + n_snap + p.n_subsamples) * st * 4 + (size_t)dyn_points * 20 + 64; };
-  uint64_t chunk = c.chunk ? c.chunk : std::max<uint64_t>(1024, std::min<uint64_t>(65536, (2ull << 30) / per_replicate_bytes(stride))) * (uint64_t)n_gpus;
+  const size_t n_dist = 1 + n_snap + p.n_subsamples;  // distributions per replicate
+  auto per_replicate_bytes = [&](uint32_t st) { return n_dist * st * 4 + (size_t)dyn_points * 20 + 64; };
+  uint64_t chunk = c.chunk ? c.chunk : std::max<uint64_t>(1024, std::min<uint64_t>(262144, (8ull << 30) / per_replicate_bytes(stride))) * (uint64_t)n_gpus;
   struct Buffers {
-    std::vector<uint32_t> stop, kmax, snap_count, hist, snap_hist, sub_hist, dyn_count;
-    std::vector<uint64_t> nminus, nplus, snap_cells;
-    std::vector<float> time, snap_time, mean, freq, entropy, dyn;
+    std::vector<uint32_t> stop, kmax, dyn_count, arena;
+    std::vector<ecdna_b200_dist_t> final_dist, snap_dist, sub_dist;
+    std::vector<uint64_t> nminus, nplus;
+    std::vector<float> time, mean, freq, entropy, dyn;
     uint64_t first = 0, n = 0;
-    uint32_t stride = 0;
   } buf[2];
   auto simulate = [&](Buffers& b, uint64_t first, uint64_t n) -> int {
     b.first = first; b.n = n;
-    b.stop.assign(n, 0); b.kmax.assign(n, 0); b.snap_count.assign(n, 0); b.dyn_count.assign(n, 0);
+    b.stop.assign(n, 0); b.kmax.assign(n, 0); b.dyn_count.assign(n, 0);
     b.nminus.assign(n, 0); b.nplus.assign(n, 0); b.time.assign(n, 0.f);
-    b.snap_cells.assign(n * n_snap, 0); b.snap_time.assign(n * n_snap, 0.f);
     b.mean.assign(n, 0.f); b.freq.assign(n, 0.f); b.entropy.assign(n, 0.f); b.dyn.assign((size_t)n * dyn_points * 5, 0.f);
+    b.final_dist.assign(n, ecdna_b200_dist_t{}); b.snap_dist.assign(n * n_snap, ecdna_b200_dist_t{});
+    b.sub_dist.assign(n * p.n_subsamples, ecdna_b200_dist_t{});
     for (int attempt = 0; attempt < 2; ++attempt) {
       p.hist_stride = stride;
-      b.stride = stride;
-      b.hist.assign((size_t)n * stride, 0);
-      b.snap_hist.assign((size_t)n * n_snap * stride, 0);
-      b.sub_hist.assign((size_t)n * p.n_subsamples * stride, 0);
       ecdna_b200_results_t r;
       std::memset(&r, 0, sizeof r);
       r.stop_reason = b.stop.data(); r.nminus = b.nminus.data(); r.nplus = b.nplus.data(); r.time = b.time.data();
-      r.kmax = b.kmax.data(); r.hist = b.hist.data();
-      if (n_snap) { r.snap_count = b.snap_count.data(); r.snap_cells = b.snap_cells.data(); r.snap_time = b.snap_time.data(); r.snap_hist = b.snap_hist.data(); }
+      r.kmax = b.kmax.data();
       if (c.summaries) { r.mean = b.mean.data(); r.frequency = b.freq.data(); r.entropy = b.entropy.data(); }
       if (c.dynamics) { r.dyn = b.dyn.data(); r.dyn_count = b.dyn_count.data(); }
-      if (p.n_subsamples) r.sub_hist = b.sub_hist.data();
-      const int rc2 = ecdna_b200_multi_run(gpus, &p, idx_begin + first, n, &r);
-      if (rc2 != ECDNA_B200_OK) { std::fprintf(stderr, "ecdna_b200_multi_run: %s\n", ecdna_b200_multi_last_error(gpus)); return 101; }
+      ecdna_b200_sparse_t sp;
+      std::memset(&sp, 0, sizeof sp);
+      sp.final_dist = b.final_dist.data();
+      if (n_snap) sp.snap_dist = b.snap_dist.data();
+      if (p.n_subsamples) sp.sub_dist = b.sub_dist.data();
+      sp.arena = b.arena.data(); sp.arena_words = b.arena.size();
+      int rc2 = ecdna_b200_multi_run_sparse(gpus, &p, idx_begin + first, n, &r, &sp);
+      if (rc2 == ECDNA_B200_ERR_ARENA) {  // the two-call pattern: the packed chunk waits on the devices for a larger arena
+        b.arena.resize(sp.arena_used + sp.arena_used / 4);
+        sp.arena = b.arena.data(); sp.arena_words = b.arena.size();
+        rc2 = ecdna_b200_multi_sparse_fetch(gpus, &sp);
+      }
+      if (rc2 != ECDNA_B200_OK) { std::fprintf(stderr, "ecdna_b200_multi_run_sparse: %s\n", ecdna_b200_multi_last_error(gpus)); return 101; }
       uint32_t top = 0;
       for (uint64_t i = 0; i < n; ++i) top = std::max(top, b.kmax[i]);
       if (top < stride) break;
@@ -509,7 +520,6 @@ int main(int argc, char** argv) {
     return 0;
   };
   auto write_files = [&](const Buffers& b) -> int {
-    const uint32_t st = b.stride;
     for (uint64_t i = 0; i < b.n; ++i) {
       const uint64_t idx = idx_begin + b.first + i;
       const std::string filename = make_filename(c, birth_death, d0, d1, idx);
@@ -518,12 +528,13 @@ int main(int argc, char** argv) {
         std::fprintf(stderr, "Overflow while segregating DNA into two daughter cells (idx %llu)\n", (unsigned long long)idx);
         return 101;
       }
-      for (uint32_t sidx = 0; sidx < b.snap_count[i] && n_snap; ++sidx) {
-        const size_t o = (size_t)i * n_snap + sidx;
-        if (verbosity > 0) std::printf("saving state for timepoint at time %s with cells %llu \n", rust_f32_to_string(b.snap_time[o]).c_str(), (unsigned long long)b.snap_cells[o]);
-        save(c, filename, b.snap_time[o], b.snap_hist.data() + o * st, st, verbosity);
+      for (size_t sidx = 0; sidx < n_snap; ++sidx) {
+        const ecdna_b200_dist_t& d = b.snap_dist[(size_t)i * n_snap + sidx];
+        if (!(d.flags & ECDNA_B200_DIST_TAKEN)) break;  // (sizes ascend: the first one not reached ends the list)
+        if (verbosity > 0) std::printf("saving state for timepoint at time %s with cells %llu \n", rust_f32_to_string(d.time).c_str(), (unsigned long long)d.cells);
+        save(c, filename, d, b.arena.data(), verbosity);
       }
-      save(c, filename, b.time[i], b.hist.data() + (size_t)i * st, st, verbosity);  // main.rs:100-109
+      save(c, filename, b.final_dist[i], b.arena.data(), verbosity);  // main.rs:100-109
       if (c.summaries) {
         const uint64_t cells_now = b.nminus[i] + b.nplus[i];
         const std::pair<const char*, float> m[] = {{"mean", b.mean[i]}, {"frequency", b.freq[i]}, {"entropy", b.entropy[i]}};
@@ -547,7 +558,7 @@ int main(int argc, char** argv) {
         f << "}";
       }
       for (uint32_t j = 0; j < p.n_subsamples; ++j)  // main.rs:110-123: one file per --subsamples size
-        save(c, filename, b.time[i], b.sub_hist.data() + ((size_t)i * p.n_subsamples + j) * st, st, verbosity);
+        save(c, filename, b.sub_dist[(size_t)i * p.n_subsamples + j], b.arena.data(), verbosity);
       if (verbosity > 0)  // main.rs:205-210
         std::printf("stop reason: %s\nnminus, nplus: [\n    %llu,\n    %llu,\n]\ntime: %s\n", kStopNames[code > 8 ? 8 : code],
                     (unsigned long long)b.nminus[i], (unsigned long long)b.nplus[i], rust_f32_to_string(b.time[i]).c_str());

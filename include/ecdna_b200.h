@@ -31,7 +31,9 @@ enum {
   ECDNA_B200_ERR_NO_DEVICE = 3,   /* no sm_100 device: the library refuses to run */
   ECDNA_B200_ERR_ALLOC = 4,
   ECDNA_B200_ERR_INTERNAL = 5,    /* the library lost track of a replicate (results incomplete); a bug */
-  ECDNA_B200_ERR_COMM = 6         /* NCCL is missing or a collective failed */
+  ECDNA_B200_ERR_COMM = 6,        /* NCCL is missing or a collective failed */
+  ECDNA_B200_ERR_ARENA = 7        /* sparse return: the caller's arena is too small; the descriptors were written,
+                                     sparse->arena_used holds the words needed: ecdna_b200_sparse_fetch() */
 };
 
 /* sosa reaction order, main.rs:140-145; live variants of EcDNAEvent, process.rs:20-29 */
@@ -276,6 +278,53 @@ int ecdna_b200_multi_run(ecdna_b200_multi* m, const ecdna_b200_params_t* params,
                          const ecdna_b200_results_t* results);
 /* times of the slowest block, counts summed over the blocks */
 int ecdna_b200_multi_get_timing(ecdna_b200_multi* m, ecdna_b200_timing_t* t);
+
+/* ---- sparse return of the distributions ----
+   The reference writes one JSON map {copy number: cells} per saved state (process.rs:31-55), whose size follows the
+   copy numbers that occur, not a fixed stride.  The dense columns hist / snap_hist / sub_hist cost hist_stride words
+   per distribution on the host and over PCIe whatever they hold (C2 with the default eleven snapshots: 12 x 4 KiB per
+   replicate for ~60 occupied bins each).  The sparse return gives, per distribution, one descriptor and the bins
+   k_min .. k_min + k_len - 1 (first to last occupied copy number >= 1) in one flat arena of 32-bit words; the
+   distributions are measured, laid out (prefix sum) and packed on the device, and only descriptors + arena cross
+   the bus.  bin 0 (cells without ecDNA) lives in the descriptor: it is far from the window of a population whose
+   copy numbers grew. */
+typedef struct {
+  uint64_t cells;   /* cells of this distribution: nminus + the bins of the window */
+  uint64_t nminus;  /* cells without ecDNA (bin 0 of the dense form) */
+  uint64_t offset;  /* first word of the window in the arena */
+  float time;       /* the clock when it was taken (snapshot: process.rs:122-145; final state and samples: the end) */
+  uint32_t k_len;   /* bins stored; 0: no cell carries ecDNA */
+  uint16_t k_min;   /* copy number of the first stored bin */
+  uint16_t flags;   /* ECDNA_B200_DIST_* */
+  uint32_t reserved;
+} ecdna_b200_dist_t;
+#define ECDNA_B200_DIST_TAKEN 0x1u     /* 0: a snapshot size the replicate never reached (everything else is 0 too) */
+#define ECDNA_B200_DIST_TRUNCATED 0x2u /* the replicate carries ECDNA_B200_FLAG_HIST_TRUNCATED: bins beyond hist_stride are missing */
+
+/* caller-owned; every descriptor pointer is optional */
+typedef struct {
+  ecdna_b200_dist_t* final_dist; /* [n]               the final distributions (main.rs:100-109) */
+  ecdna_b200_dist_t* snap_dist;  /* [n][n_snapshots]  the snapshots, in the order of params.snapshot_cells */
+  ecdna_b200_dist_t* sub_dist;   /* [n][n_subsamples] the samples of --subsamples (main.rs:110-123) */
+  uint32_t* arena;               /* [arena_words] */
+  uint64_t arena_words;          /* capacity of `arena` in 32-bit words (may be 0 to ask for the size only) */
+  uint64_t arena_used;           /* out: words the batch needs */
+} ecdna_b200_sparse_t;
+
+/* ecdna_b200_run with the distributions returned sparsely: results->hist / snap_hist / sub_hist may be NULL (they
+   are still filled when given); every other column of `results` as in ecdna_b200_run.  hist_stride still bounds the
+   copy numbers a distribution can hold (on the device only).  When sparse->arena_words < sparse->arena_used the
+   descriptors are written, the arena is not, and the call returns ECDNA_B200_ERR_ARENA: the packed batch stays on
+   the device until the context's next run, and ecdna_b200_sparse_fetch copies it into a large enough arena without
+   simulating again. */
+int ecdna_b200_run_sparse(ecdna_b200_ctx* ctx, const ecdna_b200_params_t* params, uint64_t idx_begin, uint64_t n_runs,
+                          const ecdna_b200_results_t* results, ecdna_b200_sparse_t* sparse);
+int ecdna_b200_sparse_fetch(ecdna_b200_ctx* ctx, ecdna_b200_sparse_t* sparse);
+/* the same over all GPUs of `m`: every GPU packs its block, the blocks follow each other in the arena in index
+   order and the descriptors' offsets are absolute */
+int ecdna_b200_multi_run_sparse(ecdna_b200_multi* m, const ecdna_b200_params_t* params, uint64_t idx_begin,
+                                uint64_t n_runs, const ecdna_b200_results_t* results, ecdna_b200_sparse_t* sparse);
+int ecdna_b200_multi_sparse_fetch(ecdna_b200_multi* m, ecdna_b200_sparse_t* sparse);
 
 /* ---- the one exchange step of the path: all-gather of the accepted ABC draws (abc.md:57-78) ----
    A record is ECDNA_B200_ABC_REC_HEADER + rec_bins 32-bit words:

@@ -57,7 +57,9 @@ int main(void) {
   printf("%zu %zu %zu %zu ", sizeof(ecdna_b200_params_t), sizeof(ecdna_b200_results_t), sizeof(ecdna_b200_timing_t), sizeof(ecdna_b200_replay_event_t));
   printf("%zu %zu %zu %zu %zu ", offsetof(ecdna_b200_params_t, max_cells), offsetof(ecdna_b200_params_t, seed), offsetof(ecdna_b200_params_t, init_k), offsetof(ecdna_b200_params_t, abc_thresholds), offsetof(ecdna_b200_params_t, spill_records));
   printf("%zu %zu %zu ", offsetof(ecdna_b200_params_t, slice_events), offsetof(ecdna_b200_params_t, subsample_cells), offsetof(ecdna_b200_results_t, sub_hist));
-  printf("%zu %zu %zu\\n", offsetof(ecdna_b200_results_t, hist), offsetof(ecdna_b200_timing_t, total_events), offsetof(ecdna_b200_timing_t, n_spilled));
+  printf("%zu %zu %zu ", offsetof(ecdna_b200_results_t, hist), offsetof(ecdna_b200_timing_t, total_events), offsetof(ecdna_b200_timing_t, n_spilled));
+  printf("%zu %zu %zu %zu %zu %zu ", sizeof(ecdna_b200_dist_t), offsetof(ecdna_b200_dist_t, offset), offsetof(ecdna_b200_dist_t, time), offsetof(ecdna_b200_dist_t, k_len), offsetof(ecdna_b200_dist_t, k_min), offsetof(ecdna_b200_dist_t, flags));
+  printf("%zu %zu %zu\\n", sizeof(ecdna_b200_sparse_t), offsetof(ecdna_b200_sparse_t, arena), offsetof(ecdna_b200_sparse_t, arena_used));
   return 0;
 }''')
     exe = tmp_path / "layout"
@@ -69,6 +71,9 @@ int main(void) {
             P.max_cells.offset, P.seed.offset, P.init_k.offset, P.abc_thresholds.offset, P.spill_records.offset,
             P.slice_events.offset, P.subsample_cells.offset, R.sub_hist.offset,
             R.hist.offset, T.total_events.offset, T.n_spilled.offset]
+    D, S = built.DIST_DTYPE, built.SparseT
+    want += [D.itemsize] + [D.fields[f][1] for f in ("offset", "time", "k_len", "k_min", "flags")]
+    want += [C.sizeof(S), S.arena.offset, S.arena_used.offset]
     assert got == want
 
 
