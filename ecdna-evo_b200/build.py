@@ -47,17 +47,18 @@ def _stamp(target, sources, extra=""):
         f.write(_digest(sources, extra))
 
 
-def build_debug():
+def build_debug(defines=("-DECDNA_DEBUG_BOUNDS",), suffix="dbg"):
     """libecdna_b200_dbg.so: the same sources with -DECDNA_DEBUG_BOUNDS (device-side asserts on every window
-    address, record index and output index).  Select it with ECDNA_B200_LIB=<path> (scripts/sanitize_cases.py)."""
-    out = os.path.join(PKG_DIR, "libecdna_b200_dbg.so")
+    address, record index and output index).  Select it with ECDNA_B200_LIB=<path> (scripts/sanitize_cases.py).
+    Other `defines` / `suffix` build an experimental variant next to the product library the same way."""
+    out = os.path.join(PKG_DIR, f"libecdna_b200_{suffix}.so")
     units = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith(".cu")]
     from concurrent.futures import ThreadPoolExecutor
     os.makedirs(OBJ_DIR, exist_ok=True)
 
     def one(src):
-        obj = os.path.join(OBJ_DIR, os.path.basename(src)[:-3] + ".dbg.o")
-        r = subprocess.run([_nvcc()] + NVCC_FLAGS + ["-DECDNA_DEBUG_BOUNDS", "-c", "-o", obj, src], capture_output=True, text=True)
+        obj = os.path.join(OBJ_DIR, os.path.basename(src)[:-3] + f".{suffix}.o")
+        r = subprocess.run([_nvcc()] + NVCC_FLAGS + list(defines) + ["-c", "-o", obj, src], capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
         return obj
