@@ -5,6 +5,8 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <cstdio>
+#include <cstdlib>
 #include <string>
 
 #include "ssa_kernel.cuh"
@@ -256,6 +258,21 @@ int launch_kernel(ecdna_b200_ctx* ctx, SsaArgs& a, cudaStream_t st, uint64_t max
   if constexpr (HAS_BUILDS) {
     if (minb == 3) ssa_kernel<L, GLOBAL, REPLAY, KG, 3><<<(unsigned)grid, BT, smem, st>>>(a);
     else if (minb == 4) ssa_kernel<L, GLOBAL, REPLAY, KG, 4><<<(unsigned)grid, BT, smem, st>>>(a);
+    else kern<<<(unsigned)grid, BT, smem, st>>>(a);
+  } else if constexpr (L == 1 && !GLOBAL && !REPLAY && KG == 2) {
+    // more than one warp per scheduler: issue slots bound the launch, take the build with the event loop unrolled once
+    // (measured on one box, no-unroll / unroll: 125 000 birth-death draws 285.9 / 278.4 ms; 10^4 birth-death replicates
+    // with dynamics 87.5 / 86.4 ms; 10^4 pure-birth replicates - C2 - 70.4 / 72.9 ms: the pure-birth build only when full)
+    auto kern2 = ssa_kernel<L, GLOBAL, REPLAY, KG, ECDNA_MIN_BLOCKS_L4, SPEC, 2>;
+    bool unrolled = grid * (uint64_t)warps > 4ull * (uint64_t)ctx->sm_count || SPEC == 2;
+    if (const char* e = getenv("ECDNA_B200_UNROLL")) unrolled = e[0] == '1';  // (A/B measurements)
+    if (unrolled) {
+      int b2 = 0;
+      unrolled = cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess &&
+                 cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b2, kern2, BT, smem) == cudaSuccess && b2 >= w;
+    }
+    if (getenv("ECDNA_B200_TRACE")) fprintf(stderr, "[ecdna_b200] 1-lane launch: grid %llu x %d warps, %d blocks/SM, loop unrolled: %d\n", (unsigned long long)grid, warps, w, (int)unrolled);
+    if (unrolled) kern2<<<(unsigned)grid, BT, smem, st>>>(a);
     else kern<<<(unsigned)grid, BT, smem, st>>>(a);
   } else {
     kern<<<(unsigned)grid, BT, smem, st>>>(a);

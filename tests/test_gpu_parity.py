@@ -687,3 +687,31 @@ def test_lane_cascade_is_invisible_in_the_results(pkg, ctx):
     np.testing.assert_array_equal(a.mean.view(np.uint32), b.mean.view(np.uint32))
     for i in (0, int(np.argmax(a.kmax)), 2999):
         assert_run_equal(a, i, ob.run(oracle_opts(o, o.idx_begin + i), hist_cap=512), 512, digest=False)
+
+
+@pytest.mark.parametrize("name", ["selection", "birth_death", "no_uneven"])
+def test_full_launch_build_of_lane_tiles_bit_exact(pkg, ctx, name):
+    """A launch of 1-lane tiles with more than one warp per scheduler runs the build of the kernel whose event loop
+    is unrolled once (engine.cuh: launch_kernel); pure birth, birth-death and a non-default segregation rule cover
+    its three specialisations.  Every replicate against 2-lane tiles (another kernel), some against the oracle;
+    snapshots and dynamics included."""
+    n = 24_000  # > 4 schedulers x 148 SMs x 32 lanes
+    kw = dict(CASES[name], cells=300)
+    o = pkg.SimulationOptions(runs=n, snapshots=[1, 40, 200, 300], **kw)
+    want = WANT + ("snap_count", "snap_cells", "snap_time", "snap_hist", "dyn", "dyn_count")
+    a = ctx.run(o, want=want, tile_width=1, dyn_points=20, dyn_dt=0.25)
+    b = ctx.run(o, want=want, tile_width=2, dyn_points=20, dyn_dt=0.25)
+    assert a.timing.tile_width == 1 and a.timing.grid_blocks * 2 > 4 * 148 and a.timing.n_finished == n
+    for f in want:
+        if f in ("hash", "chain"):
+            continue
+        x, y = getattr(a, f), getattr(b, f)
+        if x.dtype.kind == "f":
+            x, y = x.view(np.uint32), y.view(np.uint32)
+        np.testing.assert_array_equal(x, y, err_msg=f)
+    for i in (0, 1, n // 2, n - 1):
+        ref = ob.run(oracle_opts(o, o.idx_begin + i, snapshots=o.snapshots, dyn_points=20, dyn_dt=0.25), hist_cap=512)
+        assert_run_equal(a, i, ref, 512, digest=False)
+        assert_stats_equal(a, i, ref.hist)
+        assert int(a.dyn_count[i]) == ref.dyn_count and int(a.snap_count[i]) == ref.n_snap_taken
+        np.testing.assert_array_equal(a.dyn[i][:ref.dyn_count].view(np.uint32), ref.dyn[:ref.dyn_count].view(np.uint32))
