@@ -482,7 +482,9 @@ def abc_leg(e, args, draws_total, with_cpu, with_e2e):
     """BASELINE config 4 at full size, STRONG-scaled: rank r owns a contiguous block of the prior draws; priors
     drawn on the device, 1e5-cell birth-death runs, distances + accept in the kernel epilogue, accepted draws
     packed into records on the device and all-gathered by the library (two ncclAllGather in one group).
-    Nothing in the pass synchronises with the host until the final event."""
+    The host waits once, before the simulation is enqueued (run_device fetches the 2 KB target distribution to
+    compute its statistics and CDF); simulation, packing and exchange then follow each other on the stream
+    without any host synchronisation up to the final event."""
     m, torch, ctx = e.m, e.torch, e.ctx
     kw, _, desc = WORKLOADS["C4"]
     opts = m.SimulationOptions(save_snapshots=False, runs=draws_total, **kw)
