@@ -79,6 +79,7 @@ int ecdna_b200_multi_run(ecdna_b200_multi* m, const ecdna_b200_params_t* params,
   const uint32_t stride = params->hist_stride ? params->hist_stride : 512u;
   std::vector<int> rcs(parts, ECDNA_B200_OK);
   std::vector<std::thread> workers;
+  m->sp_valid = false;  // (a dense run replaces whatever sparse batch the devices still held)
   for (size_t g = 0; g < m->ctx.size(); ++g) m->last_count[g] = 0;
   for (int g = 0; g < parts; ++g) {
     uint64_t b, c;
