@@ -3,6 +3,7 @@ import json
 import os
 
 import numpy as np
+import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -66,3 +67,25 @@ def test_abc_csv_schema(pkg, tmp_path):
     assert rows[0]["tumour_cells"] == "1000" and rows[1]["tumour_cells"] == "0"
     assert float(rows[0]["init_mean"]) == 1.5 and rows[0]["init_cells"] == "4" and rows[0]["init_copies"] == "6"
     assert abs(float(rows[1]["ecdna"]) - 0.5) < 1e-6
+
+
+def test_cli_without_a_gpu_fails_loudly_and_parses_like_clap(tmp_path):
+    """The `ecdna` binary has no CPU path: without a B200 it exits 101 (the reference's panic code) with a message
+    and writes nothing; argument errors are caught before any device is touched and exit 2 like clap."""
+    import subprocess
+    import torch
+    import _pkg
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present; the CLI is covered by the gpu tests")
+    m = _pkg.load()
+    m.build()
+    cli = m.CLI_PATH if hasattr(m, "CLI_PATH") else os.path.join(os.path.dirname(m.__file__), "host", "ecdna")
+    out = tmp_path / "out"
+    r = subprocess.run([cli, "--runs", "2", "--cells", "100", str(out)], capture_output=True, text=True)
+    assert r.returncode == 101 and "no CPU path" in r.stderr + r.stdout
+    assert not out.exists() or not any(out.rglob("*.json"))
+    for bad in (["--segregation", "nonsense", str(out)], [], ["abc", str(out)]):
+        r = subprocess.run([cli] + bad, capture_output=True, text=True)
+        assert r.returncode == 2 and "error:" in r.stderr
+    r = subprocess.run([cli, "--version"], capture_output=True, text=True)
+    assert r.returncode == 0 and "0.26.0" in r.stdout
